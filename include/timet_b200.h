@@ -1,0 +1,158 @@
+/*
+ * timet_b200.h — C ABI of the B200-native Feature-Forwarding + Sinkhorn-Knopp library.
+ *
+ * This is the drop-in boundary for the ONE hot path of SMSD75/Timetuning that this
+ * repository replaces (BASELINE.json north_star).  The reference has no
+ * FFI layer: its boundary is a set of Python callables.  Each entry point
+ * below names the reference callable it stands behind (file:line in /root/reference);
+ * timetuning_b200/ops.py holds the Python shims with the reference signatures and
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types, no exceptions across the ABI;
+ *   - every function returns 0 on success, <0 on error; timet_last_error() (thread-local)
+ *     holds the message;
+ *   - all data pointers are DEVICE pointers on the current CUDA device, allocated and owned
+ *     by the caller (inputs, outputs and workspace; sizes from the *_workspace_bytes query);
+ *   - every launch goes to the cudaStream_t passed as `stream` (timet_stream_t == cudaStream_t);
+ *     no call synchronises the device;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns an error.
+ */
+#ifndef TIMET_B200_H
+#define TIMET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIMET_ABI_VERSION 1
+
+typedef void *timet_stream_t; /* cudaStream_t */
+typedef void *timet_comm_t;   /* opaque: owns an ncclComm_t */
+
+/* ------------------------------------------------------------------ errors / info */
+#define TIMET_OK 0
+#define TIMET_ERR_INVALID (-1)     /* bad argument                                  */
+#define TIMET_ERR_CUDA (-2)        /* CUDA runtime / driver error                   */
+#define TIMET_ERR_UNSUPPORTED (-3) /* shape outside what a kernel variant supports  */
+#define TIMET_ERR_NCCL (-4)        /* NCCL error or libnccl not loadable            */
+#define TIMET_ERR_WORKSPACE (-5)   /* workspace too small                           */
+
+const char *timet_last_error(void);
+int timet_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t timet_launch_count(void);
+
+/* ------------------------------------------------------------------ Sinkhorn-Knopp
+ * Stands behind  my_utils.sinkhorn(Q, nmb_iters, world_size)      my_utils.py:246-274
+ * and            TimeT.find_optimal_assignment(scores, eps, iters) time_tuning.py:157-168.
+ *
+ * `in` is row-major [B, K] (B local samples, K prototypes) — the physical layout of the
+ * K x B transposed view the reference passes (time_tuning.py:164).
+ *   input_kind TIMET_SK_EXP    : in = exp(scores/eps) (what sinkhorn() receives); epsilon ignored
+ *   input_kind TIMET_SK_SCORES : in = cosine scores; exp(in/epsilon) is fused into every pass
+ * q_out is row-major [B, K] float32, rows sum to 1 (my_utils.py:274).
+ * world_size > 1: `comm` must come from timet_comm_init; the K-vector of prototype marginals
+ * is all-reduced once per iteration on `stream` (my_utils.py:259-272); the sample marginal
+ * uses B * world_size (my_utils.py:257), i.e. equal B on every rank like the reference.
+ */
+#define TIMET_SK_EXP 0
+#define TIMET_SK_SCORES 1
+size_t timet_sinkhorn_workspace_bytes(int64_t B, int K);
+int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters,
+                   int world_size, timet_comm_t comm, float *q_out, void *workspace,
+                   size_t workspace_bytes, timet_stream_t stream);
+
+/* ------------------------------------------------------------------ Feature-Forwarding
+ * Stands behind  label_propagation(...)  mask_propagation.py:396-445   (one target frame)
+ *                propagate_labels(...)   mask_propagation.py:448-496   (frame loop + FIFO)
+ *                TimeT.make_seg_maps     time_tuning.py:143-154 and the per-clip loop :277-296.
+ *
+ * Layout in HBM (all row-major, contiguous):
+ *   feats   float32 [n_clips, n_frames, N, dim]         N = grid_h * grid_w, un-normalised
+ *   labels  float32 [n_clips, n_frames, N, n_channels]  channel-last soft labels; the caller
+ *           fills frame 0 (first_seg, == Sinkhorn Q rows in training); frames
+ *           t_begin..n_frames-1 are written by the library
+ *   hard    int64   [n_clips, N]  argmax over channels of the LAST frame (time_tuning.py:296);
+ *           may be NULL
+ * Context frames of target t: frame 0 plus the n_last_frames previous targets
+ * (mask_propagation.py:460,482-493).  Frames < t_begin are contexts only (their labels are
+ * caller-provided): t_begin = 1 reproduces propagate_labels; t_begin = n_frames-1 with
+ * n_last_frames >= n_frames-2 reproduces one label_propagation call on an explicit context list.
+ */
+typedef struct timet_ff_params {
+    int32_t n_clips;
+    int32_t n_frames;
+    int32_t grid_h, grid_w;   /* patch grid; the reference only supports h == w (:407) */
+    int32_t dim;              /* feature dim D */
+    int32_t n_channels;       /* C label channels */
+    int32_t n_last_frames;    /* FIFO depth (reference default 7) */
+    int32_t radius;           /* size_mask_neighborhood; 0 = no spatial restriction (:423) */
+    int32_t topk;             /* 1..16 */
+    int32_t t_begin;          /* first target frame, >= 1 */
+    float temperature;        /* 0.1 in the reference (:422) */
+    int32_t reserved;
+} timet_ff_params;
+
+/* selection engines for the affinity / top-k stage */
+#define TIMET_FF_EXACT 0 /* fp32 CUDA-core scan of every in-window key                         */
+#define TIMET_FF_TC 1    /* tcgen05 fp16 tensor-core nomination + exact fp32 re-evaluation      */
+#define TIMET_FF_AUTO 2  /* TC when the shape is supported by the tensor-core kernel, else EXACT */
+
+size_t timet_ff_workspace_bytes(const timet_ff_params *p);
+/* 1 if the tensor-core engine supports this shape (radius 1..15, n_last_frames <= 7, ...) */
+int timet_ff_tc_supported(const timet_ff_params *p);
+
+/* stage 1: L2-normalise rows (F.normalize, :418-419) -> fp32 + fp16 copies in the workspace */
+int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspace, size_t workspace_bytes,
+                     timet_stream_t stream);
+/* stage 2: per (clip, target frame, query): window mask, exp(sim/T), global top-k over all
+ * contexts with ties kept, normalised weights (:422-436) -> sparse (weight, key) lists in the workspace */
+int timet_ff_select(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+                    timet_stream_t stream);
+/* stage 3: frame-sequential weighted gather of the context labels (:439-444) and argmax */
+int timet_ff_gather(const timet_ff_params *p, float *labels, int64_t *hard, const void *workspace,
+                    size_t workspace_bytes, timet_stream_t stream);
+/* stages 1-3 */
+int timet_ff_propagate(const timet_ff_params *p, int engine, const float *feats, float *labels, int64_t *hard,
+                       void *workspace, size_t workspace_bytes, timet_stream_t stream);
+
+/* Diagnostics of the last timet_ff_select on this workspace (device -> 8 x int64 at `out`, device ptr):
+ * [0] queries, [1] selected (weight) entries, [2] queries with more than topk entries (exact ties),
+ * [3] TC candidates nominated, [4] queries re-done by the exact scan (candidate-list overflow),
+ * [5] queries whose tie set was truncated, [6..7] reserved. */
+int timet_ff_stats(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int64_t *out,
+                   timet_stream_t stream);
+/* Copy the sparse selection of (clip, t) out of the workspace for inspection / tests:
+ * weights float32 [N, kw], keys int32 [N, kw] (frame * N + patch, -1 = unused), counts int32 [N];
+ * kw = timet_ff_slots(p). */
+int timet_ff_slots(const timet_ff_params *p);
+int timet_ff_export_selection(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int clip,
+                              int t, float *weights, int32_t *keys, int32_t *counts, timet_stream_t stream);
+
+/* ------------------------------------------------------------------ small routines
+ * restrict_neighborhood(h, w, s)  mask_propagation.py:377-391 -> float32 [h*w, h*w] of 0/1
+ * norm_mask(mask)                 mask_propagation.py:363-374 -> per-channel min-max, [C, HW];
+ *                                 dtype_bytes 4 (float32) or 8 (float64)                         */
+int timet_restrict_neighborhood(int h, int w, int radius, float *mask_out, timet_stream_t stream);
+int timet_norm_mask(const void *mask, void *out, int n_channels, int64_t hw, int dtype_bytes,
+                    timet_stream_t stream);
+
+/* ------------------------------------------------------------------ multi-GPU plumbing
+ * One process per GPU (time_tuning.py:516-521,717).  Rank 0 calls timet_comm_unique_id and
+ * broadcasts the 128 bytes with whatever it has (torch.distributed in timetuning_b200/dist.py);
+ * every rank then calls timet_comm_init.  libnccl.so.2 is dlopen'ed on first use. */
+#define TIMET_UNIQUE_ID_BYTES 128
+int timet_comm_unique_id(void *id_out);
+int timet_comm_init(const void *id, int rank, int world_size, timet_comm_t *comm_out);
+int timet_comm_destroy(timet_comm_t comm);
+/* sum-all-reduce of n float32 in place on `stream` (exposed for tests of the plumbing) */
+int timet_comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, timet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIMET_B200_H */

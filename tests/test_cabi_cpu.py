@@ -1,0 +1,95 @@
+"""CPU-only checks of the boundary: the C-ABI library builds, loads, exports every symbol that
+include/timet_b200.h declares, validates arguments, and refuses to compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from timetuning_b200 import _build, _cabi, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "timet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(timet_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    lib = _cabi.lib()
+    assert os.path.isfile(_build.LIB)
+    assert lib.timet_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = header_functions()
+    assert len(declared) >= 20
+    handle = C.CDLL(_build.LIB)
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in timet_b200.h but not exported"
+    assert sorted(_cabi.EXPORTS) == declared, "ctypes prototypes out of sync with the header"
+
+
+def test_ff_params_struct_layout():
+    assert C.sizeof(_cabi.FFParams) == 48
+
+
+def test_workspace_queries_are_host_only():
+    lib = _cabi.lib()
+    p = _cabi.FFParams(32, 8, 28, 28, 384, 200, 7, 6, 5, 1, 0.1, 0)
+    n = lib.timet_ff_workspace_bytes(C.byref(p))
+    assert 100e6 < n < 2e9
+    assert lib.timet_ff_slots(C.byref(p)) == 16
+    assert lib.timet_sinkhorn_workspace_bytes(25088, 200) > 200 * 4 * 300
+
+
+@pytest.mark.parametrize("field,value", [("n_clips", 0), ("n_frames", 1), ("topk", 0), ("topk", 17), ("n_last_frames", 0),
+                                         ("t_begin", 0), ("t_begin", 8), ("radius", -1), ("temperature", 0.0), ("dim", 0)])
+def test_ff_validation(field, value):
+    lib = _cabi.lib()
+    p = _cabi.FFParams(2, 8, 28, 28, 384, 200, 7, 6, 5, 1, 0.1, 0)
+    setattr(p, field, value)
+    assert lib.timet_ff_workspace_bytes(C.byref(p)) == 0
+    assert field.split("_")[0] in lib.timet_last_error().decode() or "ff:" in lib.timet_last_error().decode()
+
+
+def test_error_codes_without_pointers():
+    lib = _cabi.lib()
+    rc = lib.timet_sinkhorn(None, 10, 10, 0, 0.05, 3, 1, None, None, None, 0, None)
+    assert rc == -1 and b"NULL" in lib.timet_last_error()
+    rc = lib.timet_restrict_neighborhood(0, 4, 1, None, None)
+    assert rc == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.sinkhorn(torch.rand(5, 7), 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.restrict_neighborhood(4, 4, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.propagate_labels_batched(torch.rand(1, 3, 16, 8), torch.rand(1, 16, 4))
+
+
+def test_spatial_resolution_duck_typing():
+    class FE:
+        spatial_resolution = 28
+
+    class Wrapper:
+        feature_extractor = FE()
+
+    assert ops._spatial_resolution(FE()) == 28
+    assert ops._spatial_resolution(Wrapper()) == 28
+
+
+def test_install_binds_reference_attributes():
+    import types
+    import timetuning_b200 as tb
+    tt, mp, mu = types.SimpleNamespace(), types.SimpleNamespace(), types.SimpleNamespace()
+    tb.install(tt, mp, mu)
+    assert tt.sinkhorn is ops.sinkhorn and tt.propagate_labels is ops.propagate_labels
+    assert mp.label_propagation is ops.label_propagation and mp.norm_mask is ops.norm_mask
+    assert mu.sinkhorn is ops.sinkhorn

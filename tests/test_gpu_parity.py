@@ -1,0 +1,275 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference-made golden
+fixtures.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+import timet_oracle as O
+import timetuning_b200 as tb
+from conftest import assert_close
+from parity import check_hard, check_soft, ff_taint
+from timetuning_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ENGINES = [tb.FF_EXACT, tb.FF_AUTO]
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+# ------------------------------------------------------------------ Sinkhorn
+@pytest.mark.parametrize("name", ["sinkhorn_b392_k200", "sinkhorn_b1000_k37", "sinkhorn_b64_k300_eps01"])
+def test_sinkhorn_golden(golden, name):
+    g = golden(name)
+    eps, iters = float(g["epsilon"]), int(g["iters"])
+    scores = cu(g["scores"])
+    q_in = torch.exp(scores / eps).t()                       # exactly what time_tuning.py:164 passes
+    keep = q_in.clone()
+    q = tb.sinkhorn(q_in, iters, 1)
+    assert q.dtype == torch.float32 and q.shape == g["q"].shape and q.is_contiguous()
+    assert torch.equal(q_in, keep), "caller's tensor must not be modified"
+    assert_close(q.cpu().numpy(), g["q"], what=name)
+    q2 = tb.sinkhorn_from_scores(scores, eps, iters)
+    assert_close(q2.cpu().numpy(), g["q"], what=name + "/fused")
+    assert (q.argmax(1).cpu().numpy() == g["q"].argmax(1)).all()
+
+
+def test_sinkhorn_contiguous_kxb_and_cpu_input(golden):
+    g = golden("sinkhorn_b392_k200")
+    q_in = torch.exp(torch.from_numpy(g["scores"]) / float(g["epsilon"])).t().contiguous()   # CPU, physically K x B
+    q = tb.sinkhorn(q_in, int(g["iters"]))
+    assert q.device.type == "cpu"
+    assert_close(q.numpy(), g["q"], what="cpu-input")
+
+
+def test_sinkhorn_full_size_properties():
+    """BASELINE configs[1] size: B = 32*784 rows, K = 200."""
+    B, K = 32 * 784, 200
+    scores = synth.cosine_scores(B, K, seed=71)
+    q = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
+    qn = q.double().cpu().numpy()
+    assert np.abs(qn.sum(1) - 1).max() < 1e-5                              # my_utils.py:274
+    ref = O.sinkhorn_scaling(scores, 0.05, 10, dtype=np.float64)
+    assert_close(qn, ref, what="full-size vs fp64 scaling oracle")
+    srt = np.sort(ref, axis=1)
+    decided = (srt[:, -1] - srt[:, -2]) > 1e-5
+    assert (qn.argmax(1) == ref.argmax(1))[decided].all()
+    # run-to-run bit reproducibility (deterministic marginal reduction)
+    q2 = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
+    assert torch.equal(q, q2)
+
+
+@pytest.mark.parametrize("iters", [0, 1, 2])
+def test_sinkhorn_few_iterations(iters):
+    scores = synth.cosine_scores(300, 64, seed=72)
+    q = tb.sinkhorn_from_scores(cu(scores), 0.05, iters).cpu().numpy()
+    ref = O.find_optimal_assignment(scores, 0.05, iters)
+    assert_close(q, ref, what=f"iters={iters}")
+
+
+def test_sinkhorn_ragged_shapes():
+    for B, K in ((1, 8), (7, 5), (33, 130), (1000, 516), (50, 1000)):
+        scores = synth.cosine_scores(B, K, seed=73 + B)
+        q = tb.sinkhorn_from_scores(cu(scores), 0.05, 3).cpu().numpy()
+        assert_close(q, O.find_optimal_assignment(scores, 0.05, 3), what=f"B={B},K={K}")
+
+
+# ------------------------------------------------------------------ small routines
+@pytest.mark.parametrize("name", ["restrict_8x8_s2", "restrict_14x14_s6", "restrict_5x9_s3"])
+def test_restrict_neighborhood(golden, name):
+    g = golden(name)
+    ref = np.unpackbits(g["mask_bits"])[: int(np.prod(g["shape"]))].reshape(g["shape"]).astype(np.float32)
+    m = tb.restrict_neighborhood(int(g["h"]), int(g["w"]), int(g["s"]))
+    assert m.dtype == torch.float32
+    assert np.array_equal(m.cpu().numpy(), ref)
+
+
+def test_restrict_neighborhood_large():
+    m = tb.restrict_neighborhood(60, 60, 12).cpu().numpy()
+    assert np.array_equal(m, O.restrict_neighborhood(60, 60, 12))
+
+
+@pytest.mark.parametrize("name", ["norm_mask", "norm_mask_f64"])
+def test_norm_mask(golden, name):
+    g = golden(name)
+    out = tb.norm_mask(cu(g["mask"]))
+    assert out.dtype == torch.from_numpy(g["out"]).dtype
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-6 if name == "norm_mask" else 1e-14, atol=0)
+
+
+# ------------------------------------------------------------------ FF: golden fixtures (reference outputs)
+class FE:
+    def __init__(self, sr):
+        self.spatial_resolution = sr
+
+
+def test_label_propagation_golden(golden):
+    g = golden("label_propagation_sr10")
+    feats, segs = g["feats"], g["segs"]
+    seg, feat_tar, mask = tb.label_propagation(int(g["s"]), int(g["topk"]), FE(int(g["sr"])), cu(feats[3]),
+                                               [cu(feats[i]).t() for i in range(3)], [cu(s) for s in segs], None, True)
+    assert seg.dtype == torch.float64 and tuple(seg.shape) == g["seg_tar"].shape
+    assert np.array_equal(feat_tar.cpu().numpy(), g["feat_tar"])
+    assert tuple(mask.shape) == (3, 100, 100)
+    check_soft(seg.cpu().numpy(), g["seg_tar"], what="label_propagation")
+
+
+@pytest.mark.parametrize("name", ["propagate_sr14_fifo", "propagate_sr12_k7", "propagate_sr9_nomask"])
+def test_propagate_labels_golden(golden, name):
+    g = golden(name)
+    out = tb.propagate_labels(int(g["n_last"]), int(g["s"]), int(g["topk"]), FE(int(g["sr"])), cu(g["feats"]),
+                              cu(g["first_seg"]), True)
+    assert isinstance(out, list) and len(out) == g["segs"].shape[0]
+    assert out[0].dtype == torch.float64 and out[0].is_cuda
+    check_soft(torch.stack(out).cpu().numpy(), g["segs"], what=name)
+
+
+def test_propagate_eval_onehot_golden(golden):
+    """Eval call pattern mask_propagation.py:821: high-res one-hot first frame, CPU tensors in."""
+    g = golden("propagate_eval_onehot")
+    first = torch.from_numpy(O.to_one_hot(g["annotation"], int(g["n_obj"]) + 1)).unsqueeze(0)
+    out = tb.propagate_labels(int(g["n_last"]), int(g["s"]), int(g["topk"]), FE(int(g["sr"])),
+                              torch.from_numpy(g["feats"]), first, True)
+    assert out[0].device.type == "cpu"
+    out = torch.stack(out).numpy()
+    check_soft(out, g["segs"], what="eval-onehot")
+    check_hard(out.argmax(1), g["segs"], what="eval-onehot")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_timet_step_cfg1_golden(golden, engine):
+    """BASELINE configs[0] on reference-made fixtures: ViT-S/16 224^2, 4-frame clips, batch 2, K=200."""
+    from timetuning_b200.step import ff_sinkhorn_step
+    g = golden("timet_step_cfg1")
+    sr = int(g["sr"])
+    bq, tq, hard, labels = ff_sinkhorn_step(cu(g["head_src"]), cu(g["head_tgt"]), cu(g["backbone"]),
+                                            cu(g["prototypes"]), engine=engine)
+    assert_close(bq.cpu().numpy(), g["batch_q"], what="batch_q")
+    assert_close(tq.cpu().numpy(), g["target_q"], what="target_q")
+    soft = labels[:, -1].permute(0, 2, 1).reshape(2, -1, sr, sr).cpu().numpy()
+    check_soft(soft, g["soft_last"], what="soft_last")
+    assert np.array_equal(hard.cpu().numpy(), g["hard"])
+    maps0 = labels[0, 1:].permute(0, 2, 1).reshape(3, -1, sr, sr).cpu().numpy()
+    check_soft(maps0, g["clip0_maps"], what="clip0 all frames")
+
+
+# ------------------------------------------------------------------ FF: against the oracle on seeded inputs
+def _oracle_clip(feats, first_cl, n_last, radius, topk, sr):
+    """feats [fs,N,D], first_cl [N,C] -> oracle segs [fs-1,C,sr,sr] (fp32 dense restatement)."""
+    C = first_cl.shape[1]
+    first = first_cl.T.reshape(1, C, sr, sr)
+    return np.stack(O.propagate_labels(n_last, radius, topk, sr, feats, first))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("sr,D,C,fs,n_last,radius,topk", [
+    (14, 384, 200, 4, 7, 6, 5),      # config 1 shapes
+    (28, 384, 200, 8, 7, 6, 5),      # config 2 shapes (2 clips)
+    (20, 96, 11, 12, 3, 4, 7),       # FIFO eviction + eval-style k
+    (16, 70, 6, 5, 7, 3, 2),         # dim not a multiple of 4/64, C not a multiple of 4
+    (12, 64, 8, 4, 7, 12, 5),        # radius >= grid: window = whole frame
+    (28, 768, 40, 3, 7, 6, 5),       # ViT-B width
+])
+def test_propagate_vs_oracle(engine, sr, D, C, fs, n_last, radius, topk):
+    bs, N = 2, sr * sr
+    feats = synth.clip_features(bs, fs, sr, D, seed=sr + D)
+    first = np.stack([synth.soft_labels(N, C, seed=100 + b) for b in range(bs)])
+    labels, hard = tb.propagate_labels_batched(cu(feats), cu(first), n_last, radius, topk, engine=engine)
+    labels = labels.cpu().numpy()
+    assert np.array_equal(labels[:, 0], first)
+    for b in range(bs):
+        ref = _oracle_clip(feats[b], first[b], n_last, radius, topk, sr)
+        _, taint, margin = ff_taint(n_last, radius, topk, sr, feats[b], first[b].T.reshape(C, sr, sr))
+        got = labels[b, 1:].transpose(0, 2, 1).reshape(fs - 1, C, sr, sr)
+        check_soft(got, ref, taint, what=f"clip {b}")
+        check_hard(hard[b].cpu().numpy(), ref[-1], taint[-1], what=f"clip {b} hard")
+
+
+def test_selection_structure_and_engine_agreement():
+    """<= k (+ties) keys per query, all inside the window and in legal context frames, weights sum
+    to 1; the tensor-core engine (when supported) reproduces the exact engine bit for bit."""
+    sr, D, C, fs, n_last, radius, topk, bs = 28, 384, 16, 8, 7, 6, 5, 3
+    N = sr * sr
+    feats = cu(synth.clip_features(bs, fs, sr, D, seed=5))
+    plan = tb.FFPlan(bs, fs, sr, sr, D, C, n_last, radius, topk)
+    plan.prepare(feats)
+    plan.select(tb.FF_EXACT)
+    st = plan.stats()
+    assert st["queries"] == bs * (fs - 1) * N and st["selected"] >= st["queries"] * topk
+    sel = {}
+    for clip in (0, bs - 1):
+        for t in (1, 4, fs - 1):
+            w, k, c = (x.cpu().numpy() for x in plan.selection(clip, t))
+            sel[(clip, t)] = (w, k, c)
+            assert (c >= topk).all() and (c <= plan.kw).all()
+            valid = np.arange(plan.kw)[None] < c[:, None]
+            assert np.allclose((w * valid).sum(1), 1, atol=1e-6)
+            assert (k[~valid] == -1).all() and (w[~valid] == 0).all()
+            frame, patch = k // N, k % N
+            ctx = O.context_frames(t, n_last)
+            assert np.isin(frame[valid], ctx).all()
+            qi = np.arange(N)[:, None]
+            assert (np.abs(patch // sr - qi // sr)[valid] <= radius).all()
+            assert (np.abs(patch % sr - qi % sr)[valid] <= radius).all()
+            assert (np.diff(w, axis=1)[valid[:, 1:]] <= 0).all(), "weights sorted descending"
+    if plan.tc_supported:
+        plan.select(tb.FF_TC)
+        for (clip, t), (w, k, c) in sel.items():
+            w2, k2, c2 = (x.cpu().numpy() for x in plan.selection(clip, t))
+            assert np.array_equal(c, c2) and np.array_equal(k, k2) and np.array_equal(w, w2), (clip, t)
+
+
+def test_duplicate_frames_keep_ties():
+    """A clip with repeated frames (the loader samples with replacement, data_loader.py:621-623) makes
+    exact affinity ties across contexts; the reference keeps them all (aff < kth -> 0, :434)."""
+    sr, D, C, fs, topk = 12, 64, 6, 4, 5
+    N = sr * sr
+    f = synth.clip_features(1, 2, sr, D, seed=9)[0]
+    feats = np.stack([f[0], f[0], f[0], f[1]])[None]           # frames 0,1,2 identical
+    first = synth.soft_labels(N, C, seed=10)[None]
+    labels, _ = tb.propagate_labels_batched(cu(feats), cu(first), 7, 4, topk, engine=tb.FF_EXACT)
+    ref = _oracle_clip(feats[0], first[0], 7, 4, topk, sr)
+    got = labels[0, 1:].permute(0, 2, 1).reshape(fs - 1, C, sr, sr).cpu().numpy()
+    check_soft(got, ref, what="duplicate frames")
+    plan = tb.FFPlan(1, fs, sr, sr, D, C, 7, 4, topk)
+    plan.prepare(cu(feats)); plan.select(tb.FF_EXACT)
+    assert plan.stats()["tie_queries"] > 0
+
+
+def test_full_batch_properties_config2():
+    """BASELINE configs[1] at full size (32 clips): size-independent properties."""
+    bs, fs, sr, D, K = 32, 8, 28, 384, 200
+    N = sr * sr
+    feats = cu(synth.clip_features(bs, fs, sr, D, seed=1))
+    first = cu(np.stack([synth.soft_labels(N, K, seed=200 + (b % 4)) for b in range(bs)]))
+    labels, hard = tb.propagate_labels_batched(feats, first, 7, 6, 5)
+    s = labels.double().sum(-1)
+    assert (s - 1).abs().max().item() < 1e-5, "label rows stay distributions (SURVEY.md §4.3)"
+    assert labels.min().item() >= 0
+    assert torch.equal(hard.view(bs, N), labels[:, -1].argmax(-1))
+    # permutation equivariance over clips
+    perm = torch.randperm(bs, generator=torch.Generator().manual_seed(0)).cuda()
+    labels_p, hard_p = tb.propagate_labels_batched(feats[perm].contiguous(), first[perm].contiguous(), 7, 6, 5)
+    assert torch.equal(labels_p, labels[perm]) and torch.equal(hard_p, hard[perm])
+    # a 2-clip slice agrees with the oracle
+    fn, fr = feats[:2].cpu().numpy(), first[:2].cpu().numpy()
+    for b in range(2):
+        ref = _oracle_clip(fn[b], fr[b], 7, 6, 5, sr)
+        _, taint, _ = ff_taint(7, 6, 5, sr, fn[b], fr[b].T.reshape(K, sr, sr))
+        got = labels[b, 1:].permute(0, 2, 1).reshape(fs - 1, K, sr, sr).cpu().numpy()
+        check_soft(got, ref, taint, what=f"cfg2 clip {b}")
+
+
+def test_davis_style_eval_config4_slice():
+    """BASELINE configs[3] shapes (480p ViT-S/8 -> 60x60 grid, radius 12, top-k 7, n_last 7, C=11),
+    first 10 frames of a synthetic video."""
+    sr, D, n_obj, fs = 60, 384, 10, 10
+    feats = synth.clip_features(1, fs, sr, D, seed=4)[0]
+    ann = synth.blob_label_map(480, n_obj, seed=6)
+    first = torch.from_numpy(O.to_one_hot(ann, n_obj + 1)).unsqueeze(0)
+    out = torch.stack(tb.propagate_labels(7, 12, 7, FE(sr), cu(feats), first.cuda(), True)).cpu().numpy()
+    ref = np.stack(O.propagate_labels(7, 12, 7, sr, feats, first.numpy()))
+    _, taint, _ = ff_taint(7, 12, 7, sr, feats, O.nearest_resize(first.numpy().astype(np.float64), sr, sr)[0])
+    check_soft(out, ref, taint, what="davis-style")
+    check_hard(out.argmax(1), ref, taint, what="davis-style hard")

@@ -1,0 +1,125 @@
+// Multi-GPU plumbing: an ncclComm_t owned by this library, bootstrapped from a unique id that
+// the host side broadcasts (timetuning_b200/dist.py).  The only data-path collective of the hot
+// path is the K-float all-reduce of the Sinkhorn prototype marginals
+// (/root/reference/my_utils.py:259-272), enqueued on the caller's stream between two passes.
+// libnccl.so.2 is dlopen'ed lazily so that the library loads (and every single-GPU path works)
+// without NCCL.  Minimal NCCL prototypes are declared here instead of including nccl.h.
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+namespace timet {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7 };
+enum { ncclSum = 0 };
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce) {
+        set_error("NCCL not available: %s", api.handle ? "missing symbols in libnccl" : dlerror());
+        return nullptr;
+    }
+    return &api;
+}
+
+struct Comm {
+    ncclComm_t nccl;
+    int rank, world_size;
+};
+
+#define TIMET_NCCL(call)                                                                          \
+    do {                                                                                          \
+        ncclResult_t r__ = (call);                                                                \
+        if (r__ != 0) {                                                                           \
+            set_error("%s failed: %s", #call, api->GetErrorString ? api->GetErrorString(r__) : "?"); \
+            return TIMET_ERR_NCCL;                                                                \
+        }                                                                                         \
+    } while (0)
+
+int comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, cudaStream_t st) {
+    NcclApi *api = nccl();
+    if (!api) return TIMET_ERR_NCCL;
+    TIMET_CHECK_ARG(comm != nullptr, "allreduce: NULL communicator");
+    Comm *c = (Comm *)comm;
+    TIMET_NCCL(api->AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, c->nccl, st));
+    return TIMET_OK;
+}
+
+}  // namespace timet
+
+using namespace timet;
+
+extern "C" {
+
+int timet_comm_unique_id(void *id_out) {
+    TIMET_CHECK_ARG(id_out != nullptr, "comm_unique_id: NULL output");
+    NcclApi *api = nccl();
+    if (!api) return TIMET_ERR_NCCL;
+    ncclUniqueId id;
+    TIMET_NCCL(api->GetUniqueId(&id));
+    memcpy(id_out, &id, TIMET_UNIQUE_ID_BYTES);
+    return TIMET_OK;
+}
+
+int timet_comm_init(const void *id, int rank, int world_size, timet_comm_t *comm_out) {
+    TIMET_CHECK_ARG(id && comm_out, "comm_init: NULL pointer");
+    TIMET_CHECK_ARG(world_size >= 1 && rank >= 0 && rank < world_size, "comm_init: bad rank %d / %d", rank, world_size);
+    NcclApi *api = nccl();
+    if (!api) return TIMET_ERR_NCCL;
+    ncclUniqueId uid;
+    memcpy(&uid, id, TIMET_UNIQUE_ID_BYTES);
+    Comm *c = new Comm{nullptr, rank, world_size};
+    ncclResult_t r = api->CommInitRank(&c->nccl, world_size, uid, rank);
+    if (r != 0) {
+        set_error("ncclCommInitRank failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+        delete c;
+        return TIMET_ERR_NCCL;
+    }
+    *comm_out = c;
+    return TIMET_OK;
+}
+
+int timet_comm_destroy(timet_comm_t comm) {
+    if (!comm) return TIMET_OK;
+    NcclApi *api = nccl();
+    if (!api) return TIMET_ERR_NCCL;
+    Comm *c = (Comm *)comm;
+    TIMET_NCCL(api->CommDestroy(c->nccl));
+    delete c;
+    return TIMET_OK;
+}
+
+int timet_comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, timet_stream_t stream) {
+    TIMET_CHECK_ARG(buf != nullptr && n >= 0, "allreduce: bad buffer");
+    return comm_allreduce_f32(comm, buf, n, (cudaStream_t)stream);
+}
+
+}

@@ -1,0 +1,139 @@
+// Shared host/device helpers of libtimet_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/timet_b200.h"
+
+namespace timet {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char *fmt, ...);
+int64_t &launch_counter();
+
+#define TIMET_CHECK_ARG(cond, ...)                 \
+    do {                                           \
+        if (!(cond)) {                             \
+            ::timet::set_error(__VA_ARGS__);       \
+            return TIMET_ERR_INVALID;              \
+        }                                          \
+    } while (0)
+
+#define TIMET_CUDA(call)                                                                        \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::timet::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return TIMET_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+// count + check a kernel launch
+#define TIMET_LAUNCHED()                                                                        \
+    do {                                                                                        \
+        ::timet::launch_counter()++;                                                            \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess) {                                                               \
+            ::timet::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return TIMET_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+int num_sms();
+
+// ------------------------------------------------------------------ FF workspace layout
+constexpr int FF_CAND_CAP = 32;     // nominated candidates per (query, epilogue group)
+constexpr int FF_CAND_LISTS = 2;    // epilogue groups per query tile
+constexpr int FF_LIST_SLOTS = 32;   // in-register sorted list = one warp
+
+struct FFLayout {
+    int N, Dp, nT, kw;               // patches, padded dim (multiple of 64), target frames, slots per query
+    int64_t rows;                    // n_clips * n_frames * N feature rows
+    int64_t queries;                 // n_clips * nT * N
+    size_t off_fn32, off_fn16, off_sel_w, off_sel_k, off_sel_cnt, off_cand, off_cand_meta, off_stats, off_redo;
+    size_t total;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static inline FFLayout ff_layout(const timet_ff_params &p) {
+    FFLayout L;
+    L.N = p.grid_h * p.grid_w;
+    L.Dp = (p.dim + 63) / 64 * 64;
+    L.nT = p.n_frames - p.t_begin;
+    L.kw = p.topk <= 8 ? 16 : 32;
+    L.rows = (int64_t)p.n_clips * p.n_frames * L.N;
+    L.queries = (int64_t)p.n_clips * L.nT * L.N;
+    size_t o = 0;
+    // +256 rows of slack: TMA boxes of the last query/key tile may run past the last row
+    L.off_fn32 = o; o = align_up(o + (size_t)(L.rows + 256) * L.Dp * sizeof(float), 1024);
+    L.off_fn16 = o; o = align_up(o + (size_t)(L.rows + 256) * L.Dp * sizeof(__half), 1024);
+    L.off_sel_w = o; o = align_up(o + (size_t)L.queries * L.kw * sizeof(float), 1024);
+    L.off_sel_k = o; o = align_up(o + (size_t)L.queries * L.kw * sizeof(int32_t), 1024);
+    L.off_sel_cnt = o; o = align_up(o + (size_t)L.queries * sizeof(int32_t), 1024);
+    L.off_cand = o; o = align_up(o + (size_t)L.queries * FF_CAND_LISTS * FF_CAND_CAP * sizeof(uint32_t), 1024);
+    L.off_cand_meta = o; o = align_up(o + (size_t)L.queries * sizeof(uint32_t), 1024);
+    L.off_stats = o; o = align_up(o + 8 * sizeof(int64_t), 1024);
+    L.off_redo = o; o = align_up(o + 1024, 1024);
+    L.total = o;
+    return L;
+}
+
+int ff_validate(const timet_ff_params *p);
+
+// stage launchers (defined in the per-stage .cu files)
+int ff_prepare_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st);
+int ff_select_exact_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
+int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
+int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
+                     cudaStream_t st);
+bool ff_tc_supported(const timet_ff_params &p);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Canonical fp32 dot product of two Dp-long rows (Dp % 4 == 0): four interleaved fmaf chains
+// over d % 4, combined as (a0 + a1) + (a2 + a3).  Every engine uses THIS order for the final
+// similarities, so the tensor-core engine and the exact scan agree bit for bit.
+__device__ __forceinline__ float dot_canonical(const float4 *__restrict__ q, const float4 *__restrict__ k, int n4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < n4; ++i) {
+        const float4 x = q[i];
+        const float4 y = __ldg(k + i);
+        a0 = fmaf(x.x, y.x, a0);
+        a1 = fmaf(x.y, y.y, a1);
+        a2 = fmaf(x.z, y.z, a2);
+        a3 = fmaf(x.w, y.w, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+// exp(sim / T) exactly as mask_propagation.py:422 evaluates it in float32
+__device__ __forceinline__ float affinity_from_sim(float sim, float temperature) {
+    return expf(__fdiv_rn(sim, temperature));
+}
+
+// First context frame after frame 0 for target t (mask_propagation.py:482-493): the FIFO holds
+// the n_last most recent targets, so contexts are {0} U {max(1, t - n_last) .. t-1}.
+__device__ __host__ __forceinline__ int ctx_lo(int t, int n_last) { return (t - n_last > 1) ? t - n_last : 1; }
+__device__ __host__ __forceinline__ int ctx_count(int t, int n_last) { return 1 + (t - ctx_lo(t, n_last)); }
+__device__ __host__ __forceinline__ int ctx_frame(int t, int n_last, int ci) {
+    return ci == 0 ? 0 : ctx_lo(t, n_last) + ci - 1;
+}
+#endif
+
+}  // namespace timet

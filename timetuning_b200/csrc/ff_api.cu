@@ -1,0 +1,130 @@
+// C ABI of the Feature-Forwarding pipeline (include/timet_b200.h).
+#include "common.cuh"
+
+namespace timet {
+
+__global__ void ff_export_kernel(const float *sel_w, const int32_t *sel_k, const int32_t *sel_cnt, int64_t q0, int N,
+                                 int kw, float *w_out, int32_t *k_out, int32_t *c_out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < N * kw) {
+        w_out[idx] = sel_w[q0 * kw + idx];
+        k_out[idx] = sel_k[q0 * kw + idx];
+    }
+    if (idx < N) c_out[idx] = sel_cnt[q0 + idx];
+}
+
+static int check_ws(const timet_ff_params *p, const void *ws, size_t bytes, FFLayout *L) {
+    int rc = ff_validate(p);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(ws != nullptr, "ff: workspace is NULL");
+    TIMET_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "ff: workspace must be 1024-byte aligned");
+    *L = ff_layout(*p);
+    if (bytes < L->total) {
+        set_error("ff: workspace %zu < %zu bytes", bytes, L->total);
+        return TIMET_ERR_WORKSPACE;
+    }
+    return TIMET_OK;
+}
+
+}  // namespace timet
+
+using namespace timet;
+
+extern "C" {
+
+size_t timet_ff_workspace_bytes(const timet_ff_params *p) {
+    if (ff_validate(p) != TIMET_OK) return 0;
+    return ff_layout(*p).total;
+}
+
+int timet_ff_slots(const timet_ff_params *p) {
+    if (ff_validate(p) != TIMET_OK) return TIMET_ERR_INVALID;
+    return ff_layout(*p).kw;
+}
+
+int timet_ff_tc_supported(const timet_ff_params *p) {
+    if (ff_validate(p) != TIMET_OK) return 0;
+    return ff_tc_supported(*p) ? 1 : 0;
+}
+
+int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspace, size_t workspace_bytes,
+                     timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(feats != nullptr, "ff_prepare: feats is NULL");
+    return ff_prepare_launch(*p, L, feats, (char *)workspace, (cudaStream_t)stream);
+}
+
+int timet_ff_select(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+                    timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(engine == TIMET_FF_EXACT || engine == TIMET_FF_TC || engine == TIMET_FF_AUTO, "ff_select: bad engine %d", engine);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    TIMET_CUDA(cudaMemsetAsync(ws + L.off_stats, 0, 8 * sizeof(int64_t) + 0, st));
+    TIMET_CUDA(cudaMemsetAsync(ws + L.off_redo, 0, 1024, st));
+    if (engine == TIMET_FF_AUTO) engine = ff_tc_supported(*p) ? TIMET_FF_TC : TIMET_FF_EXACT;
+    if (engine == TIMET_FF_TC) {
+        if (!ff_tc_supported(*p)) {
+            set_error("ff_select: tensor-core engine does not support this shape (grid %dx%d dim %d radius %d n_last %d)",
+                      p->grid_h, p->grid_w, p->dim, p->radius, p->n_last_frames);
+            return TIMET_ERR_UNSUPPORTED;
+        }
+        return ff_select_tc_launch(*p, L, ws, st);
+    }
+    return ff_select_exact_launch(*p, L, ws, st);
+}
+
+int timet_ff_gather(const timet_ff_params *p, float *labels, int64_t *hard, const void *workspace,
+                    size_t workspace_bytes, timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(labels != nullptr, "ff_gather: labels is NULL");
+    return ff_gather_launch(*p, L, labels, hard, (const char *)workspace, (cudaStream_t)stream);
+}
+
+int timet_ff_propagate(const timet_ff_params *p, int engine, const float *feats, float *labels, int64_t *hard,
+                       void *workspace, size_t workspace_bytes, timet_stream_t stream) {
+    int rc = timet_ff_prepare(p, feats, workspace, workspace_bytes, stream);
+    if (rc != TIMET_OK) return rc;
+    rc = timet_ff_select(p, engine, workspace, workspace_bytes, stream);
+    if (rc != TIMET_OK) return rc;
+    return timet_ff_gather(p, labels, hard, workspace, workspace_bytes, stream);
+}
+
+int timet_ff_stats(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int64_t *out,
+                   timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(out != nullptr, "ff_stats: out is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    TIMET_CUDA(cudaMemcpyAsync(out, (const char *)workspace + L.off_stats, 8 * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    const int64_t q = L.queries;
+    TIMET_CUDA(cudaMemcpyAsync(out, &q, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    TIMET_CUDA(cudaStreamSynchronize(st));   // `q` lives on this stack frame
+    return TIMET_OK;
+}
+
+int timet_ff_export_selection(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int clip,
+                              int t, float *weights, int32_t *keys, int32_t *counts, timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(weights && keys && counts, "ff_export_selection: NULL output");
+    TIMET_CHECK_ARG(clip >= 0 && clip < p->n_clips && t >= p->t_begin && t < p->n_frames, "ff_export_selection: bad (clip=%d, t=%d)", clip, t);
+    const char *ws = (const char *)workspace;
+    const int64_t q0 = ((int64_t)clip * L.nT + (t - p->t_begin)) * L.N;
+    const int n = L.N * L.kw;
+    ff_export_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float *>(ws + L.off_sel_w), reinterpret_cast<const int32_t *>(ws + L.off_sel_k),
+        reinterpret_cast<const int32_t *>(ws + L.off_sel_cnt), q0, L.N, L.kw, weights, keys, counts);
+    TIMET_LAUNCHED();
+    return TIMET_OK;
+}
+
+}

@@ -1,0 +1,73 @@
+// FF stage 1: L2-normalise every patch feature once per step.
+//
+// Reference: F.normalize(feat, dim=D, p=2) on the target and on ALL context frames, recomputed
+// for every target frame (/root/reference/mask_propagation.py:418-419).  Here each row is
+// normalised once: x / max(||x||_2, 1e-12) in float32 (true division, like ATen), stored
+//   fn32 [rows, Dp] float32  — operand of the exact re-evaluation (dot_canonical)
+//   fn16 [rows, Dp] float16  — K-major operand of the tcgen05 nomination GEMM (TMA-loaded)
+// Dp = dim rounded up to 64, zero padded (zeros do not change any dot product bit).
+// HBM-bound: reads 4*D, writes 6*Dp bytes per row.  One warp per row, 128-bit accesses.
+#include "common.cuh"
+
+namespace timet {
+
+__global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict__ feats, float *__restrict__ fn32,
+                                                         __half *__restrict__ fn16, int64_t rows, int dim, int Dp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const bool vec = (dim & 3) == 0;
+    for (int64_t row = warp; row < rows; row += nwarps) {
+        const float *src = feats + row * dim;
+        float ss = 0.f;
+        if (vec) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            for (int i = lane; i < (dim >> 2); i += 32) {
+                const float4 v = __ldcs(s4 + i);
+                ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
+        } else {
+            for (int i = lane; i < dim; i += 32) { const float v = src[i]; ss = fmaf(v, v, ss); }
+        }
+        ss = warp_sum(ss);
+        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+        float *d32 = fn32 + row * Dp;
+        __half *d16 = fn16 + row * Dp;
+        // Dp % 64 == 0 -> float4 / half2x2 stores are aligned
+        for (int i = lane; i < (Dp >> 2); i += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int d = i << 2;
+            if (vec) {
+                if (d < dim) v = reinterpret_cast<const float4 *>(src)[i];
+            } else {
+                if (d + 0 < dim) v.x = src[d + 0];
+                if (d + 1 < dim) v.y = src[d + 1];
+                if (d + 2 < dim) v.z = src[d + 2];
+                if (d + 3 < dim) v.w = src[d + 3];
+            }
+            v.x = __fdiv_rn(v.x, denom); v.y = __fdiv_rn(v.y, denom);
+            v.z = __fdiv_rn(v.z, denom); v.w = __fdiv_rn(v.w, denom);
+            reinterpret_cast<float4 *>(d32)[i] = v;
+            const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            reinterpret_cast<uint2 *>(d16)[i] = pk;
+        }
+    }
+}
+
+int ff_prepare_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st) {
+    float *fn32 = reinterpret_cast<float *>(ws + L.off_fn32);
+    __half *fn16 = reinterpret_cast<__half *>(ws + L.off_fn16);
+    int64_t blocks = (L.rows + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    ff_prepare_kernel<<<(int)blocks, 256, 0, st>>>(feats, fn32, fn16, L.rows, p.dim, L.Dp);
+    TIMET_LAUNCHED();
+    // the 256 slack rows behind the last frame are read by out-of-range TMA boxes: keep them finite
+    TIMET_CUDA(cudaMemsetAsync(fn16 + L.rows * L.Dp, 0, (size_t)256 * L.Dp * sizeof(__half), st));
+    return TIMET_OK;
+}
+
+}  // namespace timet

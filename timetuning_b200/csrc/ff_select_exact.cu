@@ -1,0 +1,117 @@
+// FF stage 2, EXACT engine: fp32 CUDA-core scan of every in-window key of every context.
+//
+// Reference maths per target frame (/root/reference/mask_propagation.py:418-436):
+//   sim = f^_t[i] . f^_c[j]; aff = exp(sim/0.1) * window(i,j); theta_i = k-th largest aff over all
+//   contexts; w = aff if aff >= theta_i else 0; w /= sum(w).
+// The reference materialises the [ctx*N, N] affinity in HBM and sweeps it ~12 times; here each
+// query keeps a sorted list in the registers of one warp and nothing but the <= kw survivors is
+// written.  This engine is (a) the general path for shapes the tensor-core engine does not
+// cover, (b) the re-do path for queries whose tensor-core candidate list overflowed, and
+// (c) the bit-exact yardstick for the tensor-core engine (same dot_canonical order).
+#include "ff_select.cuh"
+
+namespace timet {
+
+constexpr int EX_WARPS = 8;
+
+__global__ void __launch_bounds__(EX_WARPS * 32)
+ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float *__restrict__ fn32,
+                       float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
+                       unsigned long long *__restrict__ stats, const int32_t *__restrict__ qlist,
+                       const unsigned int *__restrict__ qcount, int64_t n_queries) {
+    extern __shared__ float4 qsm[];                       // [EX_WARPS][Dp/4]
+    __shared__ unsigned long long s_stat[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
+    __syncthreads();
+    float4 *qs = qsm + (size_t)warp * (Dp >> 2);
+    const int H = p.grid_h, W = p.grid_w;
+    const int64_t total = qlist ? (int64_t)*qcount : n_queries;
+    const int64_t nwarps = (int64_t)gridDim.x * EX_WARPS;
+    unsigned long long st_sel = 0, st_ties = 0, st_trunc = 0;
+
+    for (int64_t it = (int64_t)blockIdx.x * EX_WARPS + warp; it < total; it += nwarps) {
+        const int64_t qid = qlist ? (int64_t)qlist[it] : it;
+        const int clip = (int)(qid / ((int64_t)nT * N));
+        const int rem = (int)(qid - (int64_t)clip * nT * N);
+        const int tt = rem / N, i = rem - tt * N;
+        const int t = p.t_begin + tt;
+        const int64_t clip_row0 = (int64_t)clip * p.n_frames * N;
+
+        __syncwarp();
+        const float4 *qrow = reinterpret_cast<const float4 *>(fn32 + (clip_row0 + (int64_t)t * N + i) * Dp);
+        for (int d = lane; d < (Dp >> 2); d += 32) qs[d] = qrow[d];
+        __syncwarp();
+
+        const int qr = i / W, qc = i - qr * W;
+        int r0 = 0, r1 = H - 1, c0 = 0, c1 = W - 1;
+        if (p.radius > 0) {
+            r0 = max(qr - p.radius, 0); r1 = min(qr + p.radius, H - 1);
+            c0 = max(qc - p.radius, 0); c1 = min(qc + p.radius, W - 1);
+        }
+        const int wcols = c1 - c0 + 1, nwin = (r1 - r0 + 1) * wcols;
+
+        TopList L;
+        list_init(L);
+        const int nctx = ctx_count(t, p.n_last_frames);
+        for (int ci = 0; ci < nctx; ++ci) {
+            const int f = ctx_frame(t, p.n_last_frames, ci);
+            const float *fbase = fn32 + (clip_row0 + (int64_t)f * N) * Dp;
+            for (int m0 = 0; m0 < nwin; m0 += 32) {
+                const int m = m0 + lane;
+                const bool valid = m < nwin;
+                float aff = 0.f;
+                int32_t key = 0;
+                if (valid) {
+                    const int wr = m / wcols;
+                    const int j = (r0 + wr) * W + c0 + (m - wr * wcols);
+                    const float sim = dot_canonical(qs, reinterpret_cast<const float4 *>(fbase + (int64_t)j * Dp), Dp >> 2);
+                    aff = affinity_from_sim(sim, p.temperature);
+                    key = f * N + j;
+                }
+                list_offer(L, valid, aff, key, p.topk, lane);
+            }
+        }
+        const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);
+        st_sel += (unsigned long long)(m < kw ? m : kw);
+        st_ties += (m > p.topk);
+        st_trunc += (m > kw || L.dropped > 0);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_stat[0], st_sel);
+        atomicAdd(&s_stat[1], st_ties);
+        atomicAdd(&s_stat[2], st_trunc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!qlist) atomicAdd(&stats[0], (unsigned long long)0);   // queries counted by the host
+        if (s_stat[0]) atomicAdd(&stats[1], s_stat[0]);
+        if (s_stat[1]) atomicAdd(&stats[2], s_stat[1]);
+        if (s_stat[2]) atomicAdd(&stats[5], s_stat[2]);
+    }
+}
+
+// qlist == nullptr: every query.  Otherwise the first *qcount entries of qlist (device).
+int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, const int32_t *qlist,
+                        const unsigned int *qcount, int64_t max_items, cudaStream_t st) {
+    const size_t smem = (size_t)EX_WARPS * L.Dp * sizeof(float);
+    if (smem > 48 * 1024)
+        TIMET_CUDA(cudaFuncSetAttribute(ff_select_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (max_items + EX_WARPS - 1) / EX_WARPS;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    ff_select_exact_kernel<<<(int)blocks, EX_WARPS * 32, smem, st>>>(
+        p, L.N, L.Dp, L.nT, L.kw, reinterpret_cast<const float *>(ws + L.off_fn32),
+        reinterpret_cast<float *>(ws + L.off_sel_w), reinterpret_cast<int32_t *>(ws + L.off_sel_k),
+        reinterpret_cast<int32_t *>(ws + L.off_sel_cnt), reinterpret_cast<unsigned long long *>(ws + L.off_stats),
+        qlist, qcount, L.queries);
+    TIMET_LAUNCHED();
+    return TIMET_OK;
+}
+
+int ff_select_exact_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
+    return ff_select_exact_run(p, L, ws, nullptr, nullptr, L.queries, st);
+}
+
+}  // namespace timet

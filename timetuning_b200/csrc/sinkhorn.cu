@@ -1,0 +1,317 @@
+// Sinkhorn-Knopp balanced assignment, scaling-vector form.
+//
+// Reference: my_utils.sinkhorn (/root/reference/my_utils.py:246-274) called from
+// TimeT.find_optimal_assignment (/root/reference/time_tuning.py:157-168).
+//
+//   E = exp(S/eps)  [B, K] row-major (B samples, K prototypes)      r = 1/K, c = 1/(B*ws)
+//   pass 0      : R_i = sum_j E_ji                                  (ws>1: all-reduce R)
+//   pass p=1..n-1: a_i = r/R_i ; s_j = sum_i a_i E_ji ; b_j = c/s_j ; R_i = sum_j E_ji b_j   (all-reduce R)
+//   pass n      : a_i = r/R_i ; s_j = sum_i a_i E_ji ; Q_ji = a_i E_ji / s_j
+//
+// One streaming read of the input per pass, one write of Q: (iters+2)*B*K*4 bytes in total
+// instead of the reference's ~66 elementwise passes.  E is never stored: in SCORES mode
+// exp(S/eps) is recomputed in registers every pass (bit-identical each time).
+// The column marginals are reduced deterministically: per-CTA partials in a fixed order, the
+// last CTA to finish (atomic ticket) folds them in CTA order -> bit-reproducible runs.
+#include "common.cuh"
+
+namespace timet {
+
+constexpr int SK_THREADS = 512;
+constexpr int SK_WARPS = SK_THREADS / 32;
+constexpr int SK_MAX_V4 = 4;   // float4 chunks per lane -> K <= 512 on the vector path
+
+struct SkArgs {
+    const float *in;
+    float *q_out;
+    float *partials;      // [grid, K]
+    float *R;             // [K] marginals produced by this pass
+    const float *R_prev;  // [K] marginals of the previous pass (nullptr in pass 0)
+    unsigned int *ticket;
+    int64_t B;
+    int K;
+    float inv_eps;        // SCORES mode: 1/eps
+    float r, c;
+    int scores_mode;
+};
+
+// MODE 0: first pass (column sums only); 1: middle pass; 2: final pass (writes Q)
+template <int MODE, int NV4>
+__global__ void __launch_bounds__(SK_THREADS) sk_pass_vec(SkArgs A) {
+    extern __shared__ float smem[];
+    float *a_s = smem;                 // [K] scaling a_i = r / R_prev_i
+    float *red = smem + A.K;           // [SK_WARPS, K] per-warp marginal partials
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = A.K, K4 = K >> 2;
+
+    if (MODE != 0) {
+        for (int i = threadIdx.x; i < K; i += SK_THREADS) a_s[i] = __fdiv_rn(A.r, A.R_prev[i]);
+        __syncthreads();
+    }
+    float4 av[NV4];
+    float4 acc[NV4];
+#pragma unroll
+    for (int v = 0; v < NV4; ++v) {
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i4 = lane + 32 * v;
+        av[v] = (MODE != 0 && i4 < K4) ? reinterpret_cast<const float4 *>(a_s)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    const int64_t warps_total = (int64_t)gridDim.x * SK_WARPS;
+    for (int64_t row = (int64_t)blockIdx.x * SK_WARPS + warp; row < A.B; row += warps_total) {
+        const float4 *src = reinterpret_cast<const float4 *>(A.in + row * K);
+        float4 e[NV4];
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            e[v] = (i4 < K4) ? __ldcs(src + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (A.scores_mode) {
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                const int i4 = lane + 32 * v;
+                if (i4 < K4) {
+                    e[v].x = expf(e[v].x * A.inv_eps);
+                    e[v].y = expf(e[v].y * A.inv_eps);
+                    e[v].z = expf(e[v].z * A.inv_eps);
+                    e[v].w = expf(e[v].w * A.inv_eps);
+                }
+            }
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                acc[v].x += e[v].x; acc[v].y += e[v].y; acc[v].z += e[v].z; acc[v].w += e[v].w;
+            }
+        } else {
+            float4 p[NV4];                                  // a_i * E_ji
+            float s = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                p[v] = make_float4(e[v].x * av[v].x, e[v].y * av[v].y, e[v].z * av[v].z, e[v].w * av[v].w);
+                s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
+            }
+            s = warp_sum(s);                                // s_j = sum_i a_i E_ji
+            if (MODE == 1) {
+                const float b = __fdiv_rn(A.c, s);          // b_j = c / s_j
+#pragma unroll
+                for (int v = 0; v < NV4; ++v) {             // R_i += E_ji * b_j
+                    acc[v].x = fmaf(e[v].x, b, acc[v].x); acc[v].y = fmaf(e[v].y, b, acc[v].y);
+                    acc[v].z = fmaf(e[v].z, b, acc[v].z); acc[v].w = fmaf(e[v].w, b, acc[v].w);
+                }
+            } else {
+                const float inv = __fdiv_rn(1.f, s);
+                float4 *dst = reinterpret_cast<float4 *>(A.q_out + row * K);
+#pragma unroll
+                for (int v = 0; v < NV4; ++v) {
+                    const int i4 = lane + 32 * v;
+                    if (i4 < K4) __stcs(dst + i4, make_float4(p[v].x * inv, p[v].y * inv, p[v].z * inv, p[v].w * inv));
+                }
+            }
+        }
+    }
+    if (MODE == 2) return;
+
+    // ---- deterministic reduction of the prototype marginals
+#pragma unroll
+    for (int v = 0; v < NV4; ++v) {
+        const int i4 = lane + 32 * v;
+        if (i4 < K4) reinterpret_cast<float4 *>(red + warp * K)[i4] = acc[v];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += SK_THREADS) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < SK_WARPS; ++w) t += red[w * K + i];
+        A.partials[(int64_t)blockIdx.x * K + i] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(A.ticket, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < K; i += SK_THREADS) {
+        float t = 0.f;
+        for (unsigned int g = 0; g < gridDim.x; ++g) t += __ldcg(A.partials + (int64_t)g * K + i);
+        A.R[i] = t;
+    }
+    if (threadIdx.x == 0) *A.ticket = 0;
+}
+
+// Generic-K scalar path (K not a multiple of 4, or K > 512): lane strides over columns.
+template <int MODE>
+__global__ void __launch_bounds__(SK_THREADS) sk_pass_scalar(SkArgs A) {
+    extern __shared__ float smem[];
+    float *a_s = smem;                 // [K]
+    float *red = smem + A.K;           // [K] block marginal accumulated with shared atomics?  no: per-warp rows
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = A.K;
+    for (int i = threadIdx.x; i < K; i += SK_THREADS) {
+        a_s[i] = (MODE != 0) ? __fdiv_rn(A.r, A.R_prev[i]) : 0.f;
+        red[i] = 0.f;
+    }
+    __syncthreads();
+    // each CTA owns a contiguous block of rows; warps take rows round-robin; the per-column
+    // accumulation order inside a CTA is fixed by processing rows in warp-synchronous sweeps
+    const int64_t rows_per_cta = (A.B + gridDim.x - 1) / gridDim.x;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t row1 = (row0 + rows_per_cta < A.B) ? row0 + rows_per_cta : A.B;
+    for (int64_t base = row0; base < row1; base += SK_WARPS) {
+        const int64_t row = base + warp;
+        const bool live = row < row1;
+        float s = 0.f;
+        if (live && MODE != 0) {
+            for (int i = lane; i < K; i += 32) {
+                float e = A.in[row * K + i];
+                if (A.scores_mode) e = expf(e * A.inv_eps);
+                s += e * a_s[i];
+            }
+        }
+        s = warp_sum(s);
+        const float b = (MODE == 1) ? __fdiv_rn(A.c, s) : 1.f;
+        const float inv = (MODE == 2) ? __fdiv_rn(1.f, s) : 0.f;
+        // sweep: warps add their row to the CTA marginal one after another (fixed order)
+        for (int w = 0; w < SK_WARPS; ++w) {
+            if (w == warp && live) {
+                for (int i = lane; i < K; i += 32) {
+                    float e = A.in[row * K + i];
+                    if (A.scores_mode) e = expf(e * A.inv_eps);
+                    if (MODE == 0) red[i] += e;
+                    else if (MODE == 1) red[i] = fmaf(e, b, red[i]);
+                    else A.q_out[row * K + i] = e * a_s[i] * inv;
+                }
+            }
+            if (MODE != 2) __syncthreads();
+        }
+    }
+    if (MODE == 2) return;
+    for (int i = threadIdx.x; i < K; i += SK_THREADS) A.partials[(int64_t)blockIdx.x * K + i] = red[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(A.ticket, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < K; i += SK_THREADS) {
+        float t = 0.f;
+        for (unsigned int g = 0; g < gridDim.x; ++g) t += __ldcg(A.partials + (int64_t)g * K + i);
+        A.R[i] = t;
+    }
+    if (threadIdx.x == 0) *A.ticket = 0;
+}
+
+__global__ void sk_fill(float *p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static int sk_grid(int64_t B) {
+    const int64_t want = (B + SK_WARPS - 1) / SK_WARPS;
+    const int64_t cap = (int64_t)num_sms() * 2;        // 2 x 512-thread CTAs per SM
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <int MODE>
+static int sk_launch(const SkArgs &A, int grid, cudaStream_t st) {
+    const int K = A.K;
+    const bool vec = (K % 4 == 0) && (K <= 128 * SK_MAX_V4) && ((reinterpret_cast<uintptr_t>(A.in) & 15) == 0) &&
+                     (A.q_out == nullptr || (reinterpret_cast<uintptr_t>(A.q_out) & 15) == 0);
+    if (vec) {
+        const size_t smem = (size_t)(K + SK_WARPS * K) * sizeof(float);
+        const int nv4 = (K / 4 + 31) / 32;
+        switch (nv4) {
+            case 1: sk_pass_vec<MODE, 1><<<grid, SK_THREADS, smem, st>>>(A); break;
+            case 2: sk_pass_vec<MODE, 2><<<grid, SK_THREADS, smem, st>>>(A); break;
+            case 3: sk_pass_vec<MODE, 3><<<grid, SK_THREADS, smem, st>>>(A); break;
+            default: sk_pass_vec<MODE, 4><<<grid, SK_THREADS, smem, st>>>(A); break;
+        }
+    } else {
+        const size_t smem = (size_t)2 * K * sizeof(float);
+        if (smem > 48 * 1024) {
+            set_error("sinkhorn: K=%d too large for the scalar path", K);
+            return TIMET_ERR_UNSUPPORTED;
+        }
+        sk_pass_scalar<MODE><<<grid, SK_THREADS, smem, st>>>(A);
+    }
+    TIMET_LAUNCHED();
+    return TIMET_OK;
+}
+
+int comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, cudaStream_t st);
+
+}  // namespace timet
+
+using namespace timet;
+
+extern "C" {
+
+// workspace: partials [grid_max, K] | R ping [K] | R pong [K] | ticket
+size_t timet_sinkhorn_workspace_bytes(int64_t B, int K) {
+    (void)B;
+    if (K < 1) return 0;
+    const size_t grid_max = 2 * 160;   // >= 2 * SM count on every B200 SKU
+    return align_up((grid_max + 2) * (size_t)K * sizeof(float) + 256, 256);
+}
+
+int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
+                   timet_comm_t comm, float *q_out, void *workspace, size_t workspace_bytes, timet_stream_t stream) {
+    TIMET_CHECK_ARG(in && q_out && workspace, "sinkhorn: NULL pointer");
+    TIMET_CHECK_ARG(B >= 1 && K >= 1, "sinkhorn: bad shape B=%lld K=%d", (long long)B, K);
+    TIMET_CHECK_ARG(iters >= 0, "sinkhorn: iters=%d must be >= 0", iters);
+    TIMET_CHECK_ARG(input_kind == TIMET_SK_EXP || input_kind == TIMET_SK_SCORES, "sinkhorn: bad input_kind %d", input_kind);
+    TIMET_CHECK_ARG(input_kind == TIMET_SK_EXP || epsilon > 0.f, "sinkhorn: epsilon must be > 0");
+    TIMET_CHECK_ARG(world_size >= 1, "sinkhorn: world_size=%d must be >= 1", world_size);
+    TIMET_CHECK_ARG(world_size == 1 || comm != nullptr, "sinkhorn: world_size=%d needs a communicator", world_size);
+    if (workspace_bytes < timet_sinkhorn_workspace_bytes(B, K)) {
+        set_error("sinkhorn: workspace %zu < %zu bytes", workspace_bytes, timet_sinkhorn_workspace_bytes(B, K));
+        return TIMET_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = sk_grid(B);
+    TIMET_CHECK_ARG(grid <= 320, "sinkhorn: grid %d exceeds the workspace layout", grid);
+    float *partials = (float *)workspace;
+    float *Rbuf[2] = {partials + (size_t)320 * K, partials + (size_t)321 * K};
+    unsigned int *ticket = (unsigned int *)(partials + (size_t)322 * K);
+    TIMET_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
+
+    SkArgs A;
+    A.in = in; A.q_out = q_out; A.partials = partials; A.ticket = ticket;
+    A.B = B; A.K = K;
+    A.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
+    A.scores_mode = (input_kind == TIMET_SK_SCORES);
+    A.r = 1.0f / (float)K;
+    A.c = 1.0f / ((float)B * (float)world_size);
+
+    int rc;
+    if (iters == 0) {
+        // no scaling iterations: Q = E / rowsum(E)  (my_utils.py:274 applied to the normalised input)
+        // run the final pass with a_i = 1: feed R_prev = r so that r / R_prev = 1
+        float *ones = Rbuf[0];
+        sk_fill<<<(K + 255) / 256, 256, 0, st>>>(ones, K, A.r);
+        TIMET_LAUNCHED();
+        A.R_prev = ones; A.R = nullptr;
+        return sk_launch<2>(A, grid, st);
+    }
+    // pass 0: plain column sums
+    A.R_prev = nullptr; A.R = Rbuf[0];
+    if ((rc = sk_launch<0>(A, grid, st)) != TIMET_OK) return rc;
+    if (world_size > 1 && (rc = comm_allreduce_f32(comm, A.R, K, st)) != TIMET_OK) return rc;
+    for (int it = 1; it < iters; ++it) {
+        A.R_prev = Rbuf[(it - 1) & 1]; A.R = Rbuf[it & 1];
+        if ((rc = sk_launch<1>(A, grid, st)) != TIMET_OK) return rc;
+        if (world_size > 1 && (rc = comm_allreduce_f32(comm, A.R, K, st)) != TIMET_OK) return rc;
+    }
+    A.R_prev = Rbuf[(iters - 1) & 1]; A.R = nullptr;
+    return sk_launch<2>(A, grid, st);
+}
+
+}

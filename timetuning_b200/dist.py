@@ -1,0 +1,57 @@
+"""Multi-GPU plumbing: one process per GPU (time_tuning.py:516-521,717), clips sharded by rank,
+and the library's own NCCL communicator for the Sinkhorn marginal all-reduce
+(my_utils.py:259-272).  torch.distributed is used only to hand the 128-byte NCCL unique id
+from rank 0 to the other ranks."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi, ops
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> range:
+    """Contiguous equal shards; like the reference's equal-B assumption (my_utils.py:257) the
+    item count must divide evenly."""
+    if n_items % world_size:
+        raise ValueError(f"{n_items} clips do not shard evenly over {world_size} ranks")
+    per = n_items // world_size
+    return range(rank * per, (rank + 1) * per)
+
+
+def broadcast_bytes(payload, nbytes: int, src: int = 0, device="cpu") -> bytes:
+    """Broadcast a fixed-size byte string from `src` over the default process group."""
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    if dist.get_rank() == src:
+        buf.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(buf, src=src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def init_comm():
+    """Create the library communicator for the current default process group (no-op for 1 rank)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return None
+    if ops._comm["handle"] is not None:
+        return ops._comm["handle"]
+    lib = _cabi.lib()
+    rank, ws = dist.get_rank(), dist.get_world_size()
+    uid = None
+    if rank == 0:
+        raw = C.create_string_buffer(_cabi.UNIQUE_ID_BYTES)
+        _cabi.check(lib.timet_comm_unique_id(raw), "comm_unique_id")
+        uid = raw.raw
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    uid = broadcast_bytes(uid, _cabi.UNIQUE_ID_BYTES, 0, dev)
+    handle = C.c_void_p()
+    _cabi.check(lib.timet_comm_init(uid, rank, ws, C.byref(handle)), "comm_init")
+    ops._comm.update(handle=handle, world_size=ws, rank=rank)
+    return handle
+
+
+def destroy_comm():
+    if ops._comm["handle"] is not None:
+        _cabi.check(_cabi.lib().timet_comm_destroy(ops._comm["handle"]), "comm_destroy")
+        ops._comm.update(handle=None, world_size=1, rank=0)

@@ -1,0 +1,305 @@
+"""Host-side mirror of the reference's hot-path callables, backed by libtimet_b200.
+
+Same names, argument meaning, return conventions and error behaviour (Python exceptions) as
+
+    my_utils.sinkhorn                                   /root/reference/my_utils.py:246-274
+    mask_propagation.restrict_neighborhood              /root/reference/mask_propagation.py:377-391
+    mask_propagation.norm_mask                          /root/reference/mask_propagation.py:363-374
+    mask_propagation.label_propagation                  /root/reference/mask_propagation.py:396-445
+    mask_propagation.propagate_labels                   /root/reference/mask_propagation.py:448-496
+
+plus the additive batched entry points the training fast path uses (all clips of a batch in one
+call).  PyTorch is used for device memory and streams only; every numeric step runs in the
+hand-written sm_100a kernels behind the C ABI.  No CPU fallback: tensors living on the CPU are
+moved to the current CUDA device, and without a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import FFParams, FF_AUTO, FF_EXACT, FF_TC, SK_EXP, SK_SCORES, check
+
+AFF_TEMPERATURE = 0.1          # mask_propagation.py:422
+_comm = {"handle": None, "world_size": 1, "rank": 0}
+
+
+# --------------------------------------------------------------------------- plumbing
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("timetuning_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_cuda(x: torch.Tensor) -> torch.Tensor:
+    return x if x.is_cuda else x.to(_device(), non_blocking=True)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    # torch's caching allocator returns >= 512-byte aligned blocks; over-allocate to align to 1024
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+def _spatial_resolution(model) -> int:
+    """Duck-typed exactly like mask_propagation.py:402-405 / :452-455."""
+    fe = getattr(model, "feature_extractor", None)
+    if fe is not None and hasattr(fe, "spatial_resolution"):
+        return int(fe.spatial_resolution)
+    return int(model.spatial_resolution)
+
+
+# --------------------------------------------------------------------------- Sinkhorn
+@torch.no_grad()
+def sinkhorn(Q: torch.Tensor, nmb_iters: int, world_size: int = 1) -> torch.Tensor:
+    """Drop-in for my_utils.sinkhorn: Q is [K, B] = exp(scores/eps).t() (normally a transposed
+    view of a row-major [B, K] tensor, time_tuning.py:164).  Returns float32 [B, K]; the caller's
+    tensor is not modified (the reference clones, my_utils.py:249)."""
+    if Q.dim() != 2:
+        raise ValueError(f"sinkhorn expects a 2-D [K, B] tensor, got {tuple(Q.shape)}")
+    dev_in = Q.device
+    E = _to_cuda(Q.detach()).t()                       # [B, K]
+    if E.dtype != torch.float32:
+        E = E.float()
+    E = E.contiguous()                                 # no copy for the reference's transposed view
+    out = _sinkhorn_launch(E, SK_EXP, 1.0, nmb_iters, world_size)
+    return out if dev_in.type == "cuda" else out.to(dev_in)
+
+
+@torch.no_grad()
+def sinkhorn_from_scores(scores: torch.Tensor, epsilon: float, nmb_iters: int, world_size: int = 1) -> torch.Tensor:
+    """Fused form of TimeT.find_optimal_assignment (time_tuning.py:157-168): exp(scores/eps) is
+    evaluated inside every pass and never stored.  scores [B, K] -> Q [B, K] float32."""
+    if scores.dim() != 2:
+        raise ValueError(f"scores must be [B, K], got {tuple(scores.shape)}")
+    dev_in = scores.device
+    S = _to_cuda(scores.detach()).float().contiguous()
+    out = _sinkhorn_launch(S, SK_SCORES, float(epsilon), nmb_iters, world_size)
+    return out if dev_in.type == "cuda" else out.to(dev_in)
+
+
+def _sinkhorn_launch(x, kind, eps, iters, world_size):
+    lib = _cabi.lib()
+    B, K = x.shape
+    comm = None
+    if world_size > 1:
+        if _comm["handle"] is None or _comm["world_size"] != world_size:
+            raise RuntimeError(f"sinkhorn(world_size={world_size}) needs timetuning_b200.dist.init_comm() first "
+                               f"(communicator world size: {_comm['world_size']})")
+        comm = _comm["handle"]
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, K), dtype=torch.float32, device=x.device)
+        nbytes = lib.timet_sinkhorn_workspace_bytes(B, K)
+        ws = _workspace(nbytes, x.device)
+        check(lib.timet_sinkhorn(_ptr(x), B, K, kind, eps, int(iters), int(world_size), comm, _ptr(out), _ptr(ws),
+                                 nbytes, _stream()), "sinkhorn")
+    return out
+
+
+# --------------------------------------------------------------------------- small routines
+def restrict_neighborhood(h: int, w: int, size_mask_neighborhood: int) -> torch.Tensor:
+    """Drop-in for mask_propagation.restrict_neighborhood: float32 [h*w, h*w] 0/1 mask (built on
+    the GPU in one launch instead of a 4-deep Python loop; returned on the CUDA device)."""
+    dev = _device()
+    out = torch.empty((h * w, h * w), dtype=torch.float32, device=dev)
+    check(_cabi.lib().timet_restrict_neighborhood(int(h), int(w), int(size_mask_neighborhood), _ptr(out), _stream()),
+          "restrict_neighborhood")
+    return out
+
+
+def norm_mask(mask: torch.Tensor) -> torch.Tensor:
+    """Drop-in for mask_propagation.norm_mask: per-channel min-max normalisation of [C, h, w]."""
+    c, h, w = mask.shape
+    dev_in = mask.device
+    m = _to_cuda(mask)
+    if m.dtype not in (torch.float32, torch.float64):
+        m = m.float()
+    m = m.contiguous()
+    out = torch.empty_like(m)
+    check(_cabi.lib().timet_norm_mask(_ptr(m), _ptr(out), c, h * w, m.element_size(), _stream()), "norm_mask")
+    return out if dev_in.type == "cuda" else out.to(dev_in)
+
+
+# --------------------------------------------------------------------------- Feature-Forwarding
+class FFPlan:
+    """Shapes + workspace of one Feature-Forwarding problem batch (all clips share a shape)."""
+
+    def __init__(self, n_clips, n_frames, grid_h, grid_w, dim, n_channels, n_last_frames, radius, topk,
+                 t_begin=1, temperature=AFF_TEMPERATURE, device=None):
+        self.device = device or _device()
+        self.params = FFParams(int(n_clips), int(n_frames), int(grid_h), int(grid_w), int(dim), int(n_channels),
+                               int(n_last_frames), int(radius), int(topk), int(t_begin), float(temperature), 0)
+        lib = _cabi.lib()
+        self.nbytes = int(lib.timet_ff_workspace_bytes(C.byref(self.params)))
+        if self.nbytes == 0:
+            raise ValueError("invalid Feature-Forwarding shape: " + lib.timet_last_error().decode())
+        self.workspace = _workspace(self.nbytes, self.device)
+        self.kw = int(lib.timet_ff_slots(C.byref(self.params)))
+        self.N = int(grid_h) * int(grid_w)
+
+    @property
+    def tc_supported(self) -> bool:
+        return bool(_cabi.lib().timet_ff_tc_supported(C.byref(self.params)))
+
+    def propagate(self, feats, labels, hard=None, engine=FF_AUTO):
+        """feats fp32 [n_clips, n_frames, N, D]; labels fp32 [n_clips, n_frames, N, C] with frame(s)
+        < t_begin filled; writes frames >= t_begin in place and hard int64 [n_clips, N] if given."""
+        p = self.params
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
+        assert labels.is_cuda and labels.dtype == torch.float32 and labels.is_contiguous()
+        assert tuple(feats.shape) == (p.n_clips, p.n_frames, self.N, p.dim), tuple(feats.shape)
+        assert tuple(labels.shape) == (p.n_clips, p.n_frames, self.N, p.n_channels), tuple(labels.shape)
+        if hard is not None:
+            assert hard.is_cuda and hard.dtype == torch.int64 and hard.numel() == p.n_clips * self.N
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_propagate(C.byref(p), int(engine), _ptr(feats), _ptr(labels), _ptr(hard),
+                                                 _ptr(self.workspace), self.nbytes, _stream()), "ff_propagate")
+        return labels
+
+    def prepare(self, feats):
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_prepare(C.byref(self.params), _ptr(feats), _ptr(self.workspace), self.nbytes,
+                                               _stream()), "ff_prepare")
+
+    def select(self, engine=FF_AUTO):
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_select(C.byref(self.params), int(engine), _ptr(self.workspace), self.nbytes,
+                                              _stream()), "ff_select")
+
+    def gather(self, labels, hard=None):
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_gather(C.byref(self.params), _ptr(labels), _ptr(hard), _ptr(self.workspace),
+                                              self.nbytes, _stream()), "ff_gather")
+
+    def stats(self) -> dict:
+        out = torch.zeros(8, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_stats(C.byref(self.params), _ptr(self.workspace), self.nbytes, _ptr(out),
+                                             _stream()), "ff_stats")
+        v = out.tolist()
+        return dict(queries=v[0], selected=v[1], tie_queries=v[2], tc_candidates=v[3], redone_queries=v[4],
+                    truncated_queries=v[5])
+
+    def selection(self, clip, t):
+        """(weights [N, kw] fp32, keys [N, kw] int32 = frame*N+patch or -1, counts [N] int32)."""
+        w = torch.empty((self.N, self.kw), dtype=torch.float32, device=self.device)
+        k = torch.empty((self.N, self.kw), dtype=torch.int32, device=self.device)
+        c = torch.empty((self.N,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_export_selection(C.byref(self.params), _ptr(self.workspace), self.nbytes,
+                                                        int(clip), int(t), _ptr(w), _ptr(k), _ptr(c), _stream()),
+                  "ff_export_selection")
+        return w, k, c
+
+
+_plan_cache: dict = {}
+
+
+def _plan(*key, device):
+    k = (*key, device)
+    pl = _plan_cache.get(k)
+    if pl is None:
+        if len(_plan_cache) > 8:
+            _plan_cache.clear()
+        pl = _plan_cache[k] = FFPlan(*key, device=device)
+    return pl
+
+
+@torch.no_grad()
+def propagate_labels_batched(feats, first_labels, n_last_frames=7, size_mask_neighborhood=6, topk=5,
+                             engine=FF_AUTO, want_hard=True):
+    """Additive fast entry: every clip of a batch in one call (replaces the per-clip Python loop of
+    TimeT.get_loss, time_tuning.py:277-296).
+
+    feats [bs, fs, N, D] float32 backbone features; first_labels [bs, N, C] (Sinkhorn Q of frame 0,
+    channel-last as get_scores returns it).  Returns (labels [bs, fs, N, C] float32 with frame 0 =
+    first_labels, hard int64 [bs, sr, sr] = argmax of the last frame, or None)."""
+    feats = _to_cuda(feats).float().contiguous()
+    first_labels = _to_cuda(first_labels).float()
+    bs, fs, N, D = feats.shape
+    sr = int(round(N ** 0.5))
+    if sr * sr != N:
+        raise ValueError(f"square patch grids only (mask_propagation.py:407), got N={N}")
+    Cc = first_labels.shape[-1]
+    plan = _plan(bs, fs, sr, sr, D, Cc, n_last_frames, size_mask_neighborhood, topk, device=feats.device)
+    labels = torch.empty((bs, fs, N, Cc), dtype=torch.float32, device=feats.device)
+    labels[:, 0] = first_labels.reshape(bs, N, Cc)
+    hard = torch.empty((bs, N), dtype=torch.int64, device=feats.device) if want_hard else None
+    plan.propagate(feats, labels, hard, engine)
+    return labels, (hard.view(bs, sr, sr) if want_hard else None)
+
+
+@torch.no_grad()
+def propagate_labels(n_last_frames, size_mask_neighborhood, topk, model, frame_list, first_seg, features_exist=False):
+    """Drop-in for mask_propagation.propagate_labels (:448-496).
+
+    frame_list [fs, N, D] features (features_exist=True) or images [fs, 3, H, W]; first_seg
+    [1, C, H, W].  Returns a list of fs-1 tensors [C, sr, sr], float64 like the reference (:443,:456),
+    on the features' device."""
+    sr = _spatial_resolution(model)
+    if features_exist:
+        feats = frame_list
+    else:   # the reference runs the backbone frame by frame (:411,:467); same call, batched by frame here
+        feats = torch.stack([model(fr.unsqueeze(0), use_head=False)[0].squeeze() for fr in frame_list])
+    dev_out = feats.device
+    feats = _to_cuda(feats.detach()).float().contiguous()
+    fs, N, D = feats.shape
+    if N != sr * sr:
+        raise ValueError(f"features have {N} patches but spatial_resolution is {sr}")
+    seg = _to_cuda(first_seg.detach()).to(torch.float64)
+    seg = torch.nn.functional.interpolate(seg, size=(sr, sr), mode="nearest")            # :456
+    Cc = seg.shape[1]
+    first = seg[0].reshape(Cc, N).t().float()                                            # channel-last [N, C]
+    labels, _ = propagate_labels_batched(feats.unsqueeze(0), first.unsqueeze(0), n_last_frames,
+                                         size_mask_neighborhood, topk, want_hard=False)
+    out = labels[0, 1:].permute(0, 2, 1).reshape(fs - 1, Cc, sr, sr).to(torch.float64)
+    if dev_out.type != "cuda":
+        out = out.to(dev_out)
+    return [out[i] for i in range(fs - 1)]
+
+
+@torch.no_grad()
+def label_propagation(size_mask_neighborhood, topk, model, frame_tar, list_frame_feats, list_segs,
+                      mask_neighborhood=None, features_exist=False):
+    """Drop-in for mask_propagation.label_propagation (:396-445): one target frame against an
+    explicit context list.  frame_tar [N, D] features (or an image if features_exist=False);
+    list_frame_feats: ctx x [D, N] un-normalised; list_segs: ctx x [1, C, h, w].
+    Returns (seg_tar [1, C, h, w] float64, feat_tar [D, N], mask_neighborhood).
+    mask_neighborhood is only passed through (its content is assumed to be
+    restrict_neighborhood(h, w, size_mask_neighborhood), as propagate_labels builds it)."""
+    sr = _spatial_resolution(model)
+    if features_exist:
+        features = frame_tar
+    else:
+        features, _ = model(frame_tar.unsqueeze(0), use_head=False)
+    features = features.squeeze()
+    return_feat_tar = features.T
+    dev_out = features.device
+    ncontext = len(list_frame_feats)
+    N, D = features.shape
+    ctx = torch.stack([_to_cuda(f.detach()).float().t() for f in list_frame_feats])      # [ctx, N, D]
+    feats = torch.cat([ctx, _to_cuda(features.detach()).float().unsqueeze(0)]).contiguous()
+    segs = torch.cat([_to_cuda(s.detach()) for s in list_segs])                          # [ctx, C, h, w]
+    Cc = segs.shape[1]
+    labels = torch.empty((1, ncontext + 1, N, Cc), dtype=torch.float32, device=feats.device)
+    labels[0, :ncontext] = segs.reshape(ncontext, Cc, N).permute(0, 2, 1).float()
+    plan = FFPlan(1, ncontext + 1, sr, sr, D, Cc, max(ncontext, 1), size_mask_neighborhood, topk,
+                  t_begin=ncontext, device=feats.device)
+    plan.propagate(feats.unsqueeze(0), labels, None, FF_AUTO)
+    seg_tar = labels[0, ncontext].t().reshape(1, Cc, sr, sr).to(torch.float64)
+    if size_mask_neighborhood > 0 and mask_neighborhood is None:                         # :424-428
+        mask_neighborhood = restrict_neighborhood(sr, sr, size_mask_neighborhood).unsqueeze(0).expand(ncontext, -1, -1)
+    if dev_out.type != "cuda":
+        seg_tar = seg_tar.to(dev_out)
+    return seg_tar, return_feat_tar, mask_neighborhood
