@@ -137,3 +137,22 @@ def test_timet_step_cfg1(golden):
     assert_close(tq, g["target_q"], what="target_q", **TIGHT)
     assert_close(soft, g["soft_last"], what="soft_last", atol=1e-5, rtol=1e-5)
     assert np.array_equal(hard, g["hard"])
+
+
+def test_torch_baseline_port_matches_reference(golden):
+    """The CPU-baseline port (same ATen op sequence) reproduces the reference's outputs on config 1."""
+    import torch
+    import timet_oracle_torch as OT
+    g = golden("timet_step_cfg1")
+    T = torch.from_numpy
+    bq, tq, hard, soft = OT.ff_sinkhorn_step(T(g["head_src"]), T(g["head_tgt"]), T(g["backbone"]), T(g["prototypes"]),
+                                             int(g["sr"]))
+    assert_close(bq.numpy(), g["batch_q"], what="batch_q", atol=1e-7, rtol=1e-6)
+    assert_close(tq.numpy(), g["target_q"], what="target_q", atol=1e-7, rtol=1e-6)
+    assert_close(soft.numpy(), g["soft_last"], what="soft", atol=1e-7, rtol=1e-6)
+    assert np.array_equal(hard.numpy(), g["hard"])
+    gp = golden("propagate_sr14_fifo")
+    sr = int(gp["sr"])
+    out = OT.propagate_clip(int(gp["n_last"]), int(gp["s"]), int(gp["topk"]), sr, T(gp["feats"]),
+                            T(gp["first_seg"]).double(), OT.window_mask(sr, int(gp["s"])))
+    assert_close(torch.stack(out).numpy(), gp["segs"], what="fifo", atol=1e-7, rtol=1e-6)
