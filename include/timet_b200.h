@@ -133,6 +133,11 @@ int timet_ff_slots(const timet_ff_params *p);
 int timet_ff_export_selection(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int clip,
                               int t, float *weights, int32_t *keys, int32_t *counts, timet_stream_t stream);
 
+/* Test hook of the tensor-core engine: run ONE query tile (tile_id in the kernel's launch order) after
+ * timet_ff_prepare and dump its raw fp32 TMEM accumulators, float32 [n_key_tiles, 128, 256]. */
+int timet_debug_tc_tile(const timet_ff_params *p, void *workspace, size_t workspace_bytes, int64_t tile_id,
+                        float *dump, timet_stream_t stream);
+
 /* ------------------------------------------------------------------ small routines
  * restrict_neighborhood(h, w, s)  mask_propagation.py:377-391 -> float32 [h*w, h*w] of 0/1
  * norm_mask(mask)                 mask_propagation.py:363-374 -> per-channel min-max, [C, HW];

@@ -75,9 +75,9 @@ static inline FFLayout ff_layout(const timet_ff_params &p) {
     L.off_sel_k = o; o = align_up(o + (size_t)L.queries * L.kw * sizeof(int32_t), 1024);
     L.off_sel_cnt = o; o = align_up(o + (size_t)L.queries * sizeof(int32_t), 1024);
     L.off_cand = o; o = align_up(o + (size_t)L.queries * FF_CAND_LISTS * FF_CAND_CAP * sizeof(uint32_t), 1024);
-    L.off_cand_meta = o; o = align_up(o + (size_t)L.queries * sizeof(uint32_t), 1024);
+    L.off_cand_meta = o; o = align_up(o + (size_t)L.queries * FF_CAND_LISTS * sizeof(uint32_t), 1024);
     L.off_stats = o; o = align_up(o + 8 * sizeof(int64_t), 1024);
-    L.off_redo = o; o = align_up(o + 1024, 1024);
+    L.off_redo = o; o = align_up(o + 256 + (size_t)L.queries * sizeof(int32_t), 1024);   // count header + query ids
     L.total = o;
     return L;
 }
@@ -91,6 +91,7 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
 int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
                      cudaStream_t st);
 bool ff_tc_supported(const timet_ff_params &p);
+int ff_tc_debug_tile(const timet_ff_params &p, const FFLayout &L, char *ws, int64_t tile_id, float *dump, cudaStream_t st);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

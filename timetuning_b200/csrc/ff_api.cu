@@ -65,7 +65,7 @@ int timet_ff_select(const timet_ff_params *p, int engine, void *workspace, size_
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
     TIMET_CUDA(cudaMemsetAsync(ws + L.off_stats, 0, 8 * sizeof(int64_t) + 0, st));
-    TIMET_CUDA(cudaMemsetAsync(ws + L.off_redo, 0, 1024, st));
+    TIMET_CUDA(cudaMemsetAsync(ws + L.off_redo, 0, 256, st));
     if (engine == TIMET_FF_AUTO) engine = ff_tc_supported(*p) ? TIMET_FF_TC : TIMET_FF_EXACT;
     if (engine == TIMET_FF_TC) {
         if (!ff_tc_supported(*p)) {
@@ -125,6 +125,16 @@ int timet_ff_export_selection(const timet_ff_params *p, const void *workspace, s
         reinterpret_cast<const int32_t *>(ws + L.off_sel_cnt), q0, L.N, L.kw, weights, keys, counts);
     TIMET_LAUNCHED();
     return TIMET_OK;
+}
+
+
+int timet_debug_tc_tile(const timet_ff_params *p, void *workspace, size_t workspace_bytes, int64_t tile_id, float *dump,
+                        timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(dump != nullptr, "debug_tc_tile: dump is NULL");
+    return ff_tc_debug_tile(*p, L, (char *)workspace, tile_id, dump, (cudaStream_t)stream);
 }
 
 }

@@ -1,14 +1,535 @@
-// FF stage 2, TC engine (tcgen05 / TMEM / TMA) — placeholder until the kernel lands.
-#include "common.cuh"
+// FF stage 2, TC engine: tcgen05 / TMEM / TMA affinity GEMM with the neighbourhood window and the
+// top-k NOMINATION fused into the TMEM epilogue; the N x N affinity never exists in memory.
+//
+// Reference maths (/root/reference/mask_propagation.py:418-436): sim = f^_t f^_c^T for every context c,
+// aff = exp(sim/0.1) * window, theta_i = k-th largest over all contexts, keep aff >= theta_i, normalise.
+//
+// Precision contract.  The GEMM runs on fp16-rounded unit vectors with fp32 accumulation, so every
+// approximate similarity satisfies |sim~ - sim| <= delta (delta = 2^-10 + accumulation slack, see
+// FF_TC_DELTA).  The tensor cores only NOMINATE: a key is appended to the query's candidate list
+// when sim~ > thr, where thr is always (k-th largest sim~ seen so far) - 2*delta, a provable lower
+// bound of (final theta_i - delta).  Hence every key of the true top-k (ties included) is in the
+// list.  ff_finalize then re-evaluates the <= 64 candidates with the canonical fp32 dot product
+// (common.cuh) and applies the reference's selection exactly.  A query whose list overflowed is
+// re-done by the exact engine.  The result is bit-identical to TIMET_FF_EXACT by construction.
+//
+// One CTA per (clip, target frame, query tile of QR grid rows <= 128 queries):
+//   warp 0      TMA producer: query tile A (resident, Dp/64 swizzled 64-wide chunks) once, then a
+//               3-stage ring of key chunks B (NT = RPC*W keys x 64) for every context x key-row chunk
+//               that intersects the tile's window band (tiles outside the band are never loaded)
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=NT (<=256), K=16, fp32
+//               accumulators in TMEM, two 256-column buffers (ping-pong)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue group 0 (even key tiles), warps 8-11 epilogue group 1 (odd key tiles):
+//               tcgen05.ld 32x32b, thread = query row; window test by index arithmetic; compare with
+//               the running threshold; append packed (sim~, ctx, drow, dcol) to a per-thread list in
+//               shared memory; warp-synchronous compaction raises the threshold.
+#include "ff_select.cuh"
+#include "ptx_sm100.cuh"
 
 namespace timet {
 
-bool ff_tc_supported(const timet_ff_params &p) { (void)p; return false; }
+constexpr int TC_THREADS = 384;
+constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_NKC = 6;                  // resident query tile: Dp <= 384
+constexpr int TC_CAP = FF_CAND_CAP;            // 32 candidates per (query, epilogue group)
+constexpr float FF_TC_DELTA = 1.05e-3f;        // bound on |sim~ - sim|: fp16 RN of both unit vectors (2^-10) + fp32 accumulation
+constexpr float FF_TC_SLACK = 2.0f * FF_TC_DELTA + 3.1e-5f;   // + 2 x fixed-point quantisation (2^-17) with margin
+constexpr float TC_FIX_BIAS = 66.0f;           // sim~ + 2 in [1,3] lands in [64,128): ulp = 2^-17 -> 19-bit fixed point in the mantissa
+
+struct TcGeom {
+    int H, W, N, Dp, NKC;
+    int QR, tiles_per_frame;
+    int RPC, NT, qrows;
+    int n_clips, n_frames, nT, t_begin, n_last, radius, topk;
+    int trig;                 // compaction trigger
+    int64_t total_tiles;
+};
+
+struct __align__(8) TcSmemCtl {
+    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float tc_decode(uint32_t entry) { return (float)(entry >> 13) * (1.0f / 131072.0f) - 2.0f; }
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+constexpr uint32_t TC_SLOT_STRIDE = 128u * 4u;     // bytes between consecutive slots of one thread's list
+
+// One epilogue step, predicated (no branch): if the key is inside the window (bit BIT of wmask) and
+// sim~ > thr, append the packed candidate ((sim~ + 2) in 19-bit fixed point << 13 | code) and advance.
+template <uint32_t BIT>
+__device__ __forceinline__ void tc_offer(uint32_t &slot_addr, float v, float thr, uint32_t wmask, uint32_t code) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 u;\n\t.reg .f32 t;\n\t"
+        "and.b32 u, %3, %5;\n\t"
+        "setp.ne.b32 p, u, 0;\n\t"
+        "setp.gt.and.f32 p, %1, %2, p;\n\t"
+        "@p add.rn.f32 t, %1, 0f42840000;\n\t"     // + 66.0f
+        "@p mov.b32 u, t;\n\t"
+        "@p mad.lo.u32 u, u, 8192, %4;\n\t"
+        "@p st.shared.u32 [%0], u;\n\t"
+        "@p add.u32 %0, %0, 512;\n\t}"
+        : "+r"(slot_addr)
+        : "f"(v), "f"(thr), "r"(wmask), "r"(code), "n"(BIT)
+        : "memory");
+}
+
+// k-th largest packed entry of this thread's list (0 if fewer than k entries); warp-uniform loop bound
+__device__ __forceinline__ uint32_t tc_kth_entry(uint32_t list, int cnt, int k, int maxcnt) {
+    uint32_t prev = 0xFFFFFFFFu;
+    for (int r = 0; r < k; ++r) {
+        uint32_t m = 0;
+        for (int s = 0; s < maxcnt; ++s) {
+            const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
+            if (e < prev && e > m) m = e;
+        }
+        prev = m;
+    }
+    return prev;
+}
+
+// Raise thr from the list content and drop entries that can no longer be among the top-k.
+// Afterwards cnt <= TC_CAP/2 (entries beyond that are dropped and the query is flagged for the exact re-do).
+__device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, int &lost, int k) {
+    int maxcnt = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
+    const uint32_t kth = tc_kth_entry(list, cnt, k, maxcnt);
+    if (kth != 0u) thr = fmaxf(thr, tc_decode(kth) - FF_TC_SLACK);
+    // keep entries whose quantised value is >= thr (quantisation is already inside FF_TC_SLACK)
+    const float lim = (thr + 2.0f) * 131072.0f;
+    const uint32_t enc = (lim <= 0.f) ? 0u : ((uint32_t)lim << 13);
+    int j = 0;
+    for (int s = 0; s < maxcnt; ++s) {
+        if (s < cnt) {
+            const uint32_t e = lds_u32(list + s * TC_SLOT_STRIDE);
+            if (e >= enc) { sts_u32(list + j * TC_SLOT_STRIDE, e); ++j; }
+        }
+    }
+    if (j > TC_CAP / 2) { j = TC_CAP / 2; lost = 1; }
+    cnt = j;
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom G,
+             uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, int64_t tile_override,
+             float *__restrict__ dump) {
+    extern __shared__ uint8_t smem_raw[];
+    // carve: [A: NKC x 16 KB][B: TC_STAGES x NT*128][lists: 2 x 32 x 128 u32][ctl]; 1024-aligned for SWIZZLE_128B
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    const uint32_t b_stage_bytes = (uint32_t)G.NT * 128u;
+    uint8_t *sB = sA + (size_t)G.NKC * 16384;
+    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)TC_STAGES * b_stage_bytes);
+    TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(sList + 2 * TC_CAP * 128);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- which tile: heavy (late) target frames first
+    const int64_t tile_id = (tile_override >= 0) ? tile_override : (int64_t)blockIdx.x;
+    const int per_t = G.n_clips * G.tiles_per_frame;
+    const int tdesc = (int)(tile_id / per_t);
+    const int rem = (int)(tile_id - (int64_t)tdesc * per_t);
+    const int t = G.n_frames - 1 - tdesc;
+    const int clip = rem / G.tiles_per_frame, qt = rem - clip * G.tiles_per_frame;
+    const int qr0 = qt * G.QR;
+    const int qr1 = min(G.H - 1, qr0 + G.QR - 1);
+    const int nq = (qr1 - qr0 + 1) * G.W;
+    const int kr_lo = max(0, qr0 - G.radius), kr_hi = min(G.H - 1, qr1 + G.radius);
+    const int nchunks = (kr_hi - kr_lo + G.RPC) / G.RPC;
+    const int nctx = ctx_count(t, G.n_last);
+    const int ntiles = nctx * nchunks;
+    const int64_t clip_row0 = (int64_t)clip * G.n_frames * G.N;
+    const int q_row0 = (int)(clip_row0 + (int64_t)t * G.N + qr0 * G.W);
+
+    // ---- one-time setup
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
+        ptx::mbar_init(&ctl->a_full, 1);
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctl->tmem_full[b], 1); ptx::mbar_init(&ctl->tmem_empty[b], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<512>(&ctl->tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
+            for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, q_row0, &ctl->a_full);
+            int it = 0;
+            for (int ci = 0; ci < nctx; ++ci) {
+                const int f = ctx_frame(t, G.n_last, ci);
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int k_row0 = (int)(clip_row0 + (int64_t)f * G.N + (kr_lo + ch * G.RPC) * G.W);
+                    for (int kc = 0; kc < G.NKC; ++kc, ++it) {
+                        const int stage = it % TC_STAGES;
+                        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                        ptx::mbar_wait(&ctl->empty[stage], ph ^ 1u);
+                        ptx::mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
+                        ptx::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, kc * 64, k_row0, &ctl->full[stage]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            ptx::mbar_wait(&ctl->a_full, 0);
+            ptx::tc_fence_after();
+            const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
+            int it = 0;
+            for (int tile = 0; tile < ntiles; ++tile) {
+                const int ch = tile % nchunks;
+                const int rows_left = kr_hi + 1 - (kr_lo + ch * G.RPC);
+                const int rc = min(G.RPC, rows_left);
+                const int n_mma = min(G.NT, (rc + G.qrows - 1) / G.qrows * G.qrows * G.W);
+                const uint32_t idesc = ptx::umma_idesc_f16(128, n_mma);
+                const int buf = tile & 1;
+                const uint32_t use = (uint32_t)(tile >> 1);
+                ptx::mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
+                for (int kc = 0; kc < G.NKC; ++kc, ++it) {
+                    const int stage = it % TC_STAGES;
+                    const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                    ptx::mbar_wait(&ctl->full[stage], ph);
+                    ptx::tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = ptx::umma_desc_sw128(a_addr + kc * 16384 + k * 32);
+                        const uint64_t db = ptx::umma_desc_sw128(b_addr + stage * b_stage_bytes + k * 32);
+                        ptx::umma_f16(d_tmem, da, db, idesc, (kc | k) != 0);
+                    }
+                    ptx::umma_commit(&ctl->empty[stage]);          // frees the smem stage when the MMAs retire
+                }
+                ptx::umma_commit(&ctl->tmem_full[buf]);            // accumulator ready for its epilogue group
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue groups ===========================
+        const int g = (warp - 4) >> 2;                              // 0: even key tiles, 1: odd key tiles
+        const int qi = ((warp & 3) << 5) + lane;                    // TMEM lane == query row of the tile
+        const uint32_t lane_base = (uint32_t)((warp & 3) << 5) << 16;
+        const uint32_t list = ptx::smem_u32(sList + (size_t)g * TC_CAP * 128 + qi);   // slot s at list + s * 512 B
+        const bool valid = qi < nq;
+        const int qrow = qr0 + qi / G.W, qcol = qi % G.W;
+        const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
+        const int c_lo = qcol - G.radius;
+        const int c_lo_cl = max(c_lo, 0), c_hi_cl = min(qcol + G.radius, G.W - 1);
+        float thr = -INFINITY;
+        int cnt = 0, lost = 0;
+
+        for (int tile = g; tile < ntiles; tile += 2) {
+            const int ci = tile / nchunks, ch = tile - ci * nchunks;
+            const int kr_start = kr_lo + ch * G.RPC;
+            const int rc = min(G.RPC, kr_hi + 1 - kr_start);
+            const uint32_t use = (uint32_t)(tile >> 1);
+            ptx::mbar_wait(&ctl->tmem_full[g], use & 1u);
+            ptx::tc_fence_after();
+            const uint32_t t_acc = tmem_base + (uint32_t)g * 256u + lane_base;
+
+            if (DUMP) {
+                for (int c0 = 0; c0 < 256; c0 += 32) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(t_acc + c0, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) dump[((size_t)tile * 128 + qi) * 256 + c0 + e] = __uint_as_float(r[e]);
+                }
+            }
+
+            for (int rr = 0; rr < rc; ++rr) {
+                const int kr = kr_start + rr;
+                const bool row_ok = valid && kr >= r_lo && kr <= r_hi;
+                if (!__any_sync(0xffffffffu, row_ok)) continue;
+                const int code_row = (ci << 10) | ((kr - r_lo) << 5);
+                for (int cb = 0; cb < G.W; cb += 32) {
+                    int col0 = rr * G.W + cb;
+                    const int shift = max(0, col0 + 32 - 256);      // keep the 32-column load inside the buffer
+                    col0 -= shift;
+                    const int cb_eff = cb - shift;                  // register e holds key column cb_eff + e
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32(t_acc + (uint32_t)col0, r);
+                    // window columns of this thread inside the block -> bit mask over e
+                    const int lo = max(c_lo_cl - cb_eff, shift), hi = min(c_hi_cl - cb_eff, 31);
+                    uint32_t wmask = 0u;
+                    if (row_ok && hi >= lo) wmask = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+                    const uint32_t code0 = (uint32_t)(code_row + (cb_eff - c_lo));
+                    uint32_t slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
+                    ptx::tmem_ld_wait();
+                    // invariant: cnt <= 16 here, and each half appends at most 16 -> the 32 slots cannot overflow
+#define TC_OFFER(E) tc_offer<(1u << (E))>(slot, __uint_as_float(r[E]), thr, wmask, code0 + (E));
+                    TC_OFFER(0) TC_OFFER(1) TC_OFFER(2) TC_OFFER(3) TC_OFFER(4) TC_OFFER(5) TC_OFFER(6) TC_OFFER(7)
+                    TC_OFFER(8) TC_OFFER(9) TC_OFFER(10) TC_OFFER(11) TC_OFFER(12) TC_OFFER(13) TC_OFFER(14) TC_OFFER(15)
+                    cnt = (int)((slot - list) / TC_SLOT_STRIDE);
+                    if (__any_sync(0xffffffffu, cnt > TC_CAP / 2)) {
+                        tc_compact(list, cnt, thr, lost, G.topk);
+                        slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
+                    }
+                    TC_OFFER(16) TC_OFFER(17) TC_OFFER(18) TC_OFFER(19) TC_OFFER(20) TC_OFFER(21) TC_OFFER(22) TC_OFFER(23)
+                    TC_OFFER(24) TC_OFFER(25) TC_OFFER(26) TC_OFFER(27) TC_OFFER(28) TC_OFFER(29) TC_OFFER(30) TC_OFFER(31)
+#undef TC_OFFER
+                    cnt = (int)((slot - list) / TC_SLOT_STRIDE);
+                    if (__any_sync(0xffffffffu, cnt > TC_CAP / 2)) tc_compact(list, cnt, thr, lost, G.topk);
+                }
+            }
+            // release the accumulator buffer to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[g]);
+        }
+
+        // ---- publish the candidate list of (query, group)
+        if (!DUMP) tc_compact(list, cnt, thr, lost, G.topk);
+        if (valid && tile_override < 0) {
+            const int64_t q = ((int64_t)clip * G.nT + (t - G.t_begin)) * G.N + qr0 * G.W + qi;
+            uint32_t *dst = cand + (q * FF_CAND_LISTS + g) * TC_CAP;
+#pragma unroll
+            for (int s4 = 0; s4 < TC_CAP / 2; s4 += 4) {
+                if (s4 < cnt) {
+                    uint4 v;
+                    v.x = lds_u32(list + (s4 + 0) * TC_SLOT_STRIDE); v.y = lds_u32(list + (s4 + 1) * TC_SLOT_STRIDE);
+                    v.z = lds_u32(list + (s4 + 2) * TC_SLOT_STRIDE); v.w = lds_u32(list + (s4 + 3) * TC_SLOT_STRIDE);
+                    *reinterpret_cast<uint4 *>(dst + s4) = v;
+                }
+            }
+            cand_meta[q * FF_CAND_LISTS + g] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
+        }
+    }
+
+    // ---- teardown
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------ finalize: exact re-evaluation
+// One warp per query: lane-per-candidate canonical fp32 dot, exp, reference selection with ties.
+constexpr int FIN_WARPS = 8;
+
+__global__ void __launch_bounds__(FIN_WARPS * 32)
+ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float *__restrict__ fn32,
+                   const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_meta,
+                   float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
+                   unsigned long long *__restrict__ stats, int32_t *__restrict__ redo_list,
+                   unsigned int *__restrict__ redo_count, int64_t n_queries) {
+    extern __shared__ float4 qsm[];
+    __shared__ unsigned long long s_stat[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
+    __syncthreads();
+    float4 *qs = qsm + (size_t)warp * (Dp >> 2);
+    const int W = p.grid_w;
+    unsigned long long st_sel = 0, st_ties = 0, st_trunc = 0, st_cand = 0;
+    const int64_t nwarps = (int64_t)gridDim.x * FIN_WARPS;
+    for (int64_t qid = (int64_t)blockIdx.x * FIN_WARPS + warp; qid < n_queries; qid += nwarps) {
+        const uint32_t m0 = cand_meta[qid * 2 + 0], m1 = cand_meta[qid * 2 + 1];
+        const int c0 = (int)(m0 & 0xFFFFu), c1 = (int)(m1 & 0xFFFFu);
+        if (((m0 | m1) & 0x10000u) != 0u) {
+            if (lane == 0) redo_list[atomicAdd(redo_count, 1u)] = (int32_t)qid;
+            continue;
+        }
+        const int clip = (int)(qid / ((int64_t)nT * N));
+        const int rem = (int)(qid - (int64_t)clip * nT * N);
+        const int tt = rem / N, i = rem - tt * N;
+        const int t = p.t_begin + tt;
+        const int64_t clip_row0 = (int64_t)clip * p.n_frames * N;
+        __syncwarp();
+        const float4 *qrow = reinterpret_cast<const float4 *>(fn32 + (clip_row0 + (int64_t)t * N + i) * Dp);
+        for (int d = lane; d < (Dp >> 2); d += 32) qs[d] = qrow[d];
+        __syncwarp();
+        const int qr = i / W, qc = i - qr * W;
+        TopList L;
+        list_init(L);
+        for (int g = 0; g < 2; ++g) {
+            const int c = g ? c1 : c0;
+            const bool has = lane < c;
+            float aff = 0.f;
+            int32_t key = 0;
+            if (has) {
+                const uint32_t code = cand[(qid * 2 + g) * TC_CAP + lane] & 0x1FFFu;
+                const int ci = (int)(code >> 10), wr = (int)((code >> 5) & 31u), wc = (int)(code & 31u);
+                const int f = ctx_frame(t, p.n_last_frames, ci);
+                const int j = (qr - p.radius + wr) * W + (qc - p.radius + wc);
+                const float sim = dot_canonical(qs, reinterpret_cast<const float4 *>(fn32 + (clip_row0 + (int64_t)f * N + j) * Dp), Dp >> 2);
+                aff = affinity_from_sim(sim, p.temperature);
+                key = f * N + j;
+            }
+            list_offer(L, has, aff, key, p.topk, lane);
+        }
+        const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);
+        st_sel += (unsigned long long)(m < kw ? m : kw);
+        st_ties += (m > p.topk);
+        st_trunc += (m > kw);
+        st_cand += (unsigned long long)(c0 + c1);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_stat[0], st_sel);
+        atomicAdd(&s_stat[1], st_ties);
+        atomicAdd(&s_stat[2], st_trunc);
+        atomicAdd(&s_stat[3], st_cand);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_stat[0]) atomicAdd(&stats[1], s_stat[0]);
+        if (s_stat[1]) atomicAdd(&stats[2], s_stat[1]);
+        if (s_stat[3]) atomicAdd(&stats[3], s_stat[3]);
+        if (s_stat[2]) atomicAdd(&stats[5], s_stat[2]);
+    }
+}
+
+__global__ void ff_redo_count_kernel(const unsigned int *redo_count, unsigned long long *stats) {
+    stats[4] = *redo_count;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return TIMET_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)Dp * sizeof(__half)};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld Dp=%d box_rows=%d)", (int)r, (long long)rows, Dp, box_rows);
+        return TIMET_ERR_CUDA;
+    }
+    return TIMET_OK;
+}
+
+static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
+    const int W = p.grid_w, H = p.grid_h;
+    if (p.radius < 1 || p.radius > 15) return false;
+    if (p.n_last_frames > 7 || p.topk > 8) return false;   // 3-bit context slot in the packed candidate; k + ties must fit 16 slots
+    if (W > 128 || L.Dp > 64 * TC_MAX_NKC) return false;
+    int g = W, b = 16;
+    while (b) { const int tmp = g % b; g = b; b = tmp; }   // gcd(W, 16)
+    const int qrows = 16 / g;
+    if (qrows * W > 256) return false;
+    const int RPC = (256 / W) / qrows * qrows;
+    G->H = H; G->W = W; G->N = L.N; G->Dp = L.Dp; G->NKC = L.Dp / 64;
+    G->QR = (128 / W) < H ? (128 / W) : H;
+    G->tiles_per_frame = (H + G->QR - 1) / G->QR;
+    G->RPC = RPC; G->NT = RPC * W; G->qrows = qrows;
+    G->n_clips = p.n_clips; G->n_frames = p.n_frames; G->nT = L.nT; G->t_begin = p.t_begin;
+    G->n_last = p.n_last_frames; G->radius = p.radius; G->topk = p.topk;
+    const int side = 2 * p.radius + 1;
+    G->trig = 16; (void)side;
+    G->total_tiles = (int64_t)p.n_clips * L.nT * G->tiles_per_frame;
+    return true;
+}
+
+static size_t tc_smem_bytes(const TcGeom &G) {
+    return 1024 + (size_t)G.NKC * 16384 + (size_t)TC_STAGES * G.NT * 128 + (size_t)2 * TC_CAP * 128 * 4 + sizeof(TcSmemCtl) + 64;
+}
+
+bool ff_tc_supported(const timet_ff_params &p) {
+    TcGeom G;
+    const FFLayout L = ff_layout(p);
+    if (!tc_geometry(p, L, &G)) return false;
+    return tc_smem_bytes(G) <= 227 * 1024;
+}
+
+int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, const int32_t *qlist,
+                        const unsigned int *qcount, int64_t max_items, cudaStream_t st);
 
 int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
-    (void)p; (void)L; (void)ws; (void)st;
-    set_error("tensor-core engine not built");
-    return TIMET_ERR_UNSUPPORTED;
+    TcGeom G;
+    if (!tc_geometry(p, L, &G)) {
+        set_error("tensor-core engine: unsupported shape");
+        return TIMET_ERR_UNSUPPORTED;
+    }
+    const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
+    CUtensorMap map_a, map_b;
+    int rc;
+    if ((rc = make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+    if ((rc = make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
+    const size_t smem = tc_smem_bytes(G);
+    TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t *cand = reinterpret_cast<uint32_t *>(ws + L.off_cand);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_cand_meta);
+    ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, -1, nullptr);
+    TIMET_LAUNCHED();
+
+    unsigned int *redo_count = reinterpret_cast<unsigned int *>(ws + L.off_redo);
+    int32_t *redo_list = reinterpret_cast<int32_t *>(ws + L.off_redo + 256);
+    const size_t fsmem = (size_t)FIN_WARPS * L.Dp * sizeof(float);
+    int64_t blocks = (L.queries + FIN_WARPS - 1) / FIN_WARPS;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    ff_finalize_kernel<<<(int)blocks, FIN_WARPS * 32, fsmem, st>>>(
+        p, L.N, L.Dp, L.nT, L.kw, reinterpret_cast<const float *>(ws + L.off_fn32), cand, meta,
+        reinterpret_cast<float *>(ws + L.off_sel_w), reinterpret_cast<int32_t *>(ws + L.off_sel_k),
+        reinterpret_cast<int32_t *>(ws + L.off_sel_cnt), reinterpret_cast<unsigned long long *>(ws + L.off_stats),
+        redo_list, redo_count, L.queries);
+    TIMET_LAUNCHED();
+    // overflowed queries: exact scan (device-side count; a fixed small grid loops over the list)
+    if ((rc = ff_select_exact_run(p, L, ws, redo_list, redo_count, (int64_t)num_sms() * 8 * 8, st)) != TIMET_OK) return rc;
+    ff_redo_count_kernel<<<1, 1, 0, st>>>(redo_count, reinterpret_cast<unsigned long long *>(ws + L.off_stats));
+    TIMET_LAUNCHED();
+    return TIMET_OK;
+}
+
+// debug: run ONE query tile and dump its raw fp32 accumulators [ntiles, 128, 256] (tests only)
+int ff_tc_debug_tile(const timet_ff_params &p, const FFLayout &L, char *ws, int64_t tile_id, float *dump, cudaStream_t st) {
+    TcGeom G;
+    if (!tc_geometry(p, L, &G)) {
+        set_error("tensor-core engine: unsupported shape");
+        return TIMET_ERR_UNSUPPORTED;
+    }
+    TIMET_CHECK_ARG(tile_id >= 0 && tile_id < G.total_tiles, "debug tile %lld out of range", (long long)tile_id);
+    const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
+    CUtensorMap map_a, map_b;
+    int rc;
+    if ((rc = make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+    if ((rc = make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
+    const size_t smem = tc_smem_bytes(G);
+    TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ff_tc_kernel<true><<<1, TC_THREADS, smem, st>>>(map_a, map_b, G, nullptr, nullptr, tile_id, dump);
+    TIMET_LAUNCHED();
+    return TIMET_OK;
 }
 
 }  // namespace timet
