@@ -106,21 +106,39 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// Canonical fp32 dot product of two Dp-long rows (Dp % 4 == 0): four interleaved fmaf chains
-// over d % 4, combined as (a0 + a1) + (a2 + a3).  Every engine uses THIS order for the final
-// similarities, so the tensor-core engine and the exact scan agree bit for bit.
-__device__ __forceinline__ float dot_canonical(const float4 *__restrict__ q, const float4 *__restrict__ k, int n4) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < n4; ++i) {
-        const float4 x = q[i];
-        const float4 y = __ldg(k + i);
-        a0 = fmaf(x.x, y.x, a0);
-        a1 = fmaf(x.y, y.y, a1);
-        a2 = fmaf(x.z, y.z, a2);
-        a3 = fmaf(x.w, y.w, a3);
+// Canonical fp32 dot product of two Dp-long rows (Dp % 64 == 0, n4 = Dp/4 float4 elements).
+// DEFINITION (every engine reproduces it bit for bit, so the tensor-core engine and the exact scan agree):
+//   partial[l], l = 0..31 : one fmaf chain over the float4 elements i = l, l+32, l+64, ... in that order,
+//                           components x, y, z, w in that order;
+//   result                : xor-butterfly tree  v[l] += v[l ^ 16]; v[l] += v[l ^ 8]; ... ; v[l] += v[l ^ 1].
+// dot_canonical_warp: the 32 lanes of a warp each own one partial (coalesced 512-byte row segments).
+// dot_canonical_seq : one thread emulates all 32 partials and the same tree (lane-per-key scans).
+__device__ __forceinline__ float fma4_chain(float acc, const float4 x, const float4 y) {
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+    acc = fmaf(x.z, y.z, acc);
+    return fmaf(x.w, y.w, acc);
+}
+__device__ __forceinline__ float dot_canonical_warp(const float4 *__restrict__ q, const float4 *__restrict__ k, int n4, int lane) {
+    float acc = 0.f;
+    for (int i = lane; i < n4; i += 32) acc = fma4_chain(acc, q[i], __ldg(k + i));
+    return warp_sum(acc);
+}
+__device__ __forceinline__ float dot_canonical_seq(const float4 *__restrict__ q, const float4 *__restrict__ k, int n4) {
+    float acc[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+    for (int base = 0; base < n4; base += 32) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+            if (base + l < n4) acc[l] = fma4_chain(acc[l], q[base + l], __ldg(k + base + l));
     }
-    return (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < o; ++l) acc[l] += acc[l + o];
+    }
+    return acc[0];
 }
 
 // exp(sim / T) exactly as mask_propagation.py:422 evaluates it in float32

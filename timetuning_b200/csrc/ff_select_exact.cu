@@ -65,7 +65,7 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
                 if (valid) {
                     const int wr = m / wcols;
                     const int j = (r0 + wr) * W + c0 + (m - wr * wcols);
-                    const float sim = dot_canonical(qs, reinterpret_cast<const float4 *>(fbase + (int64_t)j * Dp), Dp >> 2);
+                    const float sim = dot_canonical_seq(qs, reinterpret_cast<const float4 *>(fbase + (int64_t)j * Dp), Dp >> 2);
                     aff = affinity_from_sim(sim, p.temperature);
                     key = f * N + j;
                 }

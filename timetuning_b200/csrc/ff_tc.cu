@@ -32,6 +32,7 @@ namespace timet {
 constexpr int TC_THREADS = 384;
 constexpr int TC_STAGES = 3;
 constexpr int TC_MAX_NKC = 6;                  // resident query tile: Dp <= 384
+constexpr int TC_CLIP_GROUP = 8;                // clips whose tiles are launched together (L2 locality)
 constexpr int TC_CAP = FF_CAND_CAP;            // 32 candidates per (query, epilogue group)
 constexpr float FF_TC_DELTA = 1.05e-3f;        // bound on |sim~ - sim|: fp16 RN of both unit vectors (2^-10) + fp32 accumulation
 constexpr float FF_TC_SLACK = 2.0f * FF_TC_DELTA + 3.1e-5f;   // + 2 x fixed-point quantisation (2^-17) with margin
@@ -82,38 +83,41 @@ __device__ __forceinline__ void tc_offer(uint32_t &slot_addr, float v, float thr
         : "memory");
 }
 
-// k-th largest packed entry of this thread's list (0 if fewer than k entries); warp-uniform loop bound
-__device__ __forceinline__ uint32_t tc_kth_entry(uint32_t list, int cnt, int k, int maxcnt) {
-    uint32_t prev = 0xFFFFFFFFu;
-    for (int r = 0; r < k; ++r) {
-        uint32_t m = 0;
-        for (int s = 0; s < maxcnt; ++s) {
-            const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
-            if (e < prev && e > m) m = e;
-        }
-        prev = m;
-    }
-    return prev;
-}
-
 // Raise thr from the list content and drop entries that can no longer be among the top-k.
+// One pass over the list keeps the 8 largest packed entries in sorted registers (max/min chain), so the
+// k-th largest (k <= 8) is read off directly.  Warp-synchronous; loop bounds are warp-uniform.
 // Afterwards cnt <= TC_CAP/2 (entries beyond that are dropped and the query is flagged for the exact re-do).
 __device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, int &lost, int k) {
     int maxcnt = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
-    const uint32_t kth = tc_kth_entry(list, cnt, k, maxcnt);
+    uint32_t top[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) top[j] = 0u;
+#pragma unroll 4
+    for (int s = 0; s < maxcnt; ++s) {
+        uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t hi = max(e, top[j]);
+            e = min(e, top[j]);
+            top[j] = hi;
+        }
+    }
+    uint32_t kth = top[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) kth = (k - 1 == j) ? top[j] : kth;
     if (kth != 0u) thr = fmaxf(thr, tc_decode(kth) - FF_TC_SLACK);
     // keep entries whose quantised value is >= thr (quantisation is already inside FF_TC_SLACK)
     const float lim = (thr + 2.0f) * 131072.0f;
     const uint32_t enc = (lim <= 0.f) ? 0u : ((uint32_t)lim << 13);
-    int j = 0;
+    uint32_t dst = list;
+#pragma unroll 4
     for (int s = 0; s < maxcnt; ++s) {
-        if (s < cnt) {
-            const uint32_t e = lds_u32(list + s * TC_SLOT_STRIDE);
-            if (e >= enc) { sts_u32(list + j * TC_SLOT_STRIDE, e); ++j; }
-        }
+        const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
+        if (s < cnt && e >= enc) { sts_u32(dst, e); dst += TC_SLOT_STRIDE; }
     }
+    int j = (int)((dst - list) / TC_SLOT_STRIDE);
     if (j > TC_CAP / 2) { j = TC_CAP / 2; lost = 1; }
     cnt = j;
 }
@@ -136,11 +140,17 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 
     // ---- which tile: heavy (late) target frames first
     const int64_t tile_id = (tile_override >= 0) ? tile_override : (int64_t)blockIdx.x;
-    const int per_t = G.n_clips * G.tiles_per_frame;
-    const int tdesc = (int)(tile_id / per_t);
-    const int rem = (int)(tile_id - (int64_t)tdesc * per_t);
+    // launch order: groups of TC_CLIP_GROUP clips (their frames stay L2-resident while the group runs),
+    // inside a group the heavy (late) target frames first
+    const int per_clip = G.nT * G.tiles_per_frame;
+    const int grp = (int)(tile_id / ((int64_t)TC_CLIP_GROUP * per_clip));
+    const int grp_clips = min(TC_CLIP_GROUP, G.n_clips - grp * TC_CLIP_GROUP);
+    const int in_grp = (int)(tile_id - (int64_t)grp * TC_CLIP_GROUP * per_clip);
+    const int per_t = grp_clips * G.tiles_per_frame;
+    const int tdesc = in_grp / per_t;
+    const int rem = in_grp - tdesc * per_t;
     const int t = G.n_frames - 1 - tdesc;
-    const int clip = rem / G.tiles_per_frame, qt = rem - clip * G.tiles_per_frame;
+    const int clip = grp * TC_CLIP_GROUP + rem / G.tiles_per_frame, qt = rem % G.tiles_per_frame;
     const int qr0 = qt * G.QR;
     const int qr1 = min(G.H - 1, qr0 + G.QR - 1);
     const int nq = (qr1 - qr0 + 1) * G.W;
@@ -359,24 +369,29 @@ ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float
         for (int d = lane; d < (Dp >> 2); d += 32) qs[d] = qrow[d];
         __syncwarp();
         const int qr = i / W, qc = i - qr * W;
+        // lane j owns candidate j of the concatenated lists (c0 + c1 <= 32)
+        const int nc = c0 + c1;
+        const bool has = lane < nc;
+        int32_t key = 0, krow = 0;
+        if (has) {
+            const uint32_t code = (lane < c0 ? cand[(qid * 2 + 0) * TC_CAP + lane]
+                                             : cand[(qid * 2 + 1) * TC_CAP + (lane - c0)]) & 0x1FFFu;
+            const int ci = (int)(code >> 10), wr = (int)((code >> 5) & 31u), wc = (int)(code & 31u);
+            const int f = ctx_frame(t, p.n_last_frames, ci);
+            const int j = (qr - p.radius + wr) * W + (qc - p.radius + wc);
+            key = f * N + j;
+            krow = (int32_t)(clip_row0 + key);
+        }
+        // warp-cooperative canonical dot per candidate (coalesced 512-byte segments of the key row)
+        float my_sim = 0.f;
+        for (int c = 0; c < nc; ++c) {
+            const int32_t row = __shfl_sync(0xffffffffu, krow, c);
+            const float sim = dot_canonical_warp(qs, reinterpret_cast<const float4 *>(fn32 + (int64_t)row * Dp), Dp >> 2, lane);
+            if (lane == c) my_sim = sim;
+        }
         TopList L;
         list_init(L);
-        for (int g = 0; g < 2; ++g) {
-            const int c = g ? c1 : c0;
-            const bool has = lane < c;
-            float aff = 0.f;
-            int32_t key = 0;
-            if (has) {
-                const uint32_t code = cand[(qid * 2 + g) * TC_CAP + lane] & 0x1FFFu;
-                const int ci = (int)(code >> 10), wr = (int)((code >> 5) & 31u), wc = (int)(code & 31u);
-                const int f = ctx_frame(t, p.n_last_frames, ci);
-                const int j = (qr - p.radius + wr) * W + (qc - p.radius + wc);
-                const float sim = dot_canonical(qs, reinterpret_cast<const float4 *>(fn32 + (clip_row0 + (int64_t)f * N + j) * Dp), Dp >> 2);
-                aff = affinity_from_sim(sim, p.temperature);
-                key = f * N + j;
-            }
-            list_offer(L, has, aff, key, p.topk, lane);
-        }
+        list_offer(L, has, has ? affinity_from_sim(my_sim, p.temperature) : 0.f, key, p.topk, lane);
         const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);
         st_sel += (unsigned long long)(m < kw ? m : kw);
         st_ties += (m > p.topk);
