@@ -24,6 +24,8 @@
 //               tcgen05.ld 32x32b, thread = query row; window test by index arithmetic; compare with
 //               the running threshold; append packed (sim~, ctx, drow, dcol) to a per-thread list in
 //               shared memory; warp-synchronous compaction raises the threshold.
+#include <stdlib.h>
+
 #include "ff_select.cuh"
 #include "ptx_sm100.cuh"
 
@@ -44,6 +46,7 @@ struct TcGeom {
     int RPC, NT, qrows;
     int n_clips, n_frames, nT, t_begin, n_last, radius, topk;
     int trig;                 // compaction trigger
+    int flags;                // debug (env TIMET_TC_FLAGS): 1 = epilogue releases tiles unscanned, 2 = scan but never append
     int64_t total_tiles;
 };
 
@@ -243,7 +246,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
         const int c_lo = qcol - G.radius;
         const int c_lo_cl = max(c_lo, 0), c_hi_cl = min(qcol + G.radius, G.W - 1);
-        float thr = -INFINITY;
+        float thr = (G.flags & 2) ? INFINITY : -INFINITY;
         int cnt = 0, lost = 0;
 
         for (int tile = g; tile < ntiles; tile += 2) {
@@ -265,7 +268,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 }
             }
 
-            for (int rr = 0; rr < rc; ++rr) {
+            for (int rr = 0; rr < ((G.flags & 1) ? 0 : rc); ++rr) {
                 const int kr = kr_start + rr;
                 const bool row_ok = valid && kr >= r_lo && kr <= r_hi;
                 if (!__any_sync(0xffffffffu, row_ok)) continue;
@@ -472,6 +475,8 @@ static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) 
     G->n_last = p.n_last_frames; G->radius = p.radius; G->topk = p.topk;
     const int side = 2 * p.radius + 1;
     G->trig = 16; (void)side;
+    const char *fl = getenv("TIMET_TC_FLAGS");
+    G->flags = fl ? atoi(fl) : 0;
     G->total_tiles = (int64_t)p.n_clips * L.nT * G->tiles_per_frame;
     return true;
 }
