@@ -13,6 +13,8 @@
 // exp(S/eps) is recomputed in registers every pass (bit-identical each time).
 // The column marginals are reduced deterministically: per-CTA partials in a fixed order, the
 // last CTA to finish (atomic ticket) folds them in CTA order -> bit-reproducible runs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace timet {
@@ -34,6 +36,32 @@ struct SkArgs {
     float r, c;
     int scores_mode;
 };
+
+// Fixed-order, coalesced fold of per-CTA marginal partials [n_parts, K] -> out[K].
+// Column i is split over P = min(NT / K, 8) threads: thread (i, j) adds parts g = j, j+P, ... in order
+// (consecutive threads read consecutive columns: full 128-byte lines), then j = 0..P-1 are added in order.
+// out[i] = r / sum if r != 0 (the scaling a_i), else the sum itself.  `scratch` holds >= 8*K floats.
+template <int NT>
+__device__ __forceinline__ void fold_partials(const float *partials, unsigned int n_parts, int K, float *scratch,
+                                              float *out, float r) {
+    int P = NT / K;
+    P = P > 8 ? 8 : (P < 1 ? 1 : P);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < K * P; idx += NT) {
+        const int j = idx / K, i = idx - j * K;
+        float t = 0.f;
+#pragma unroll 4
+        for (unsigned int g = j; g < n_parts; g += P) t += __ldcg(partials + (size_t)g * K + i);
+        scratch[j * K + i] = t;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += NT) {
+        float t = scratch[i];
+        for (int j = 1; j < P; ++j) t += scratch[j * K + i];
+        out[i] = (r != 0.f) ? __fdiv_rn(r, t) : t;
+    }
+    __syncthreads();
+}
 
 // MODE 0: first pass (column sums only); 1: middle pass; 2: final pass (writes Q)
 template <int MODE, int NV4>
@@ -135,11 +163,7 @@ __global__ void __launch_bounds__(SK_THREADS) sk_pass_vec(SkArgs A) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int i = threadIdx.x; i < K; i += SK_THREADS) {
-        float t = 0.f;
-        for (unsigned int g = 0; g < gridDim.x; ++g) t += __ldcg(A.partials + (int64_t)g * K + i);
-        A.R[i] = t;
-    }
+    fold_partials<SK_THREADS>(A.partials, gridDim.x, K, red, A.R, 0.f);
     if (threadIdx.x == 0) *A.ticket = 0;
 }
 
@@ -148,7 +172,7 @@ template <int MODE>
 __global__ void __launch_bounds__(SK_THREADS) sk_pass_scalar(SkArgs A) {
     extern __shared__ float smem[];
     float *a_s = smem;                 // [K]
-    float *red = smem + A.K;           // [K] block marginal accumulated with shared atomics?  no: per-warp rows
+    float *red = smem + A.K;           // [K] CTA marginal; the tail fold reuses red[0 .. 8K) as scratch
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.K;
@@ -201,17 +225,159 @@ __global__ void __launch_bounds__(SK_THREADS) sk_pass_scalar(SkArgs A) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int i = threadIdx.x; i < K; i += SK_THREADS) {
-        float t = 0.f;
-        for (unsigned int g = 0; g < gridDim.x; ++g) t += __ldcg(A.partials + (int64_t)g * K + i);
-        A.R[i] = t;
-    }
+    fold_partials<SK_THREADS>(A.partials, gridDim.x, K, red, A.R, 0.f);
     if (threadIdx.x == 0) *A.ticket = 0;
 }
 
 __global__ void sk_fill(float *p, int n, float v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident variant (single GPU): ONE cooperative launch for the whole call.  Each CTA keeps its
+// block of rows of E = exp(S/eps) in shared memory across all iterations (config 2: 25 088 x 200
+// fp32 = 20 MB over 148 SMs = 136 KB per CTA), so HBM traffic is the compulsory read of S and write
+// of Q.  Per iteration: one sweep over shared memory, per-CTA marginal partials to global
+// (double-buffered), a grid barrier, and a fixed-order fold of all partials by every CTA
+// (bit-reproducible, identical on every CTA).
+constexpr int SKR_THREADS = 1024;
+constexpr int SKR_WARPS = SKR_THREADS / 32;
+
+struct SkResArgs {
+    const float *in;
+    float *q_out;
+    float *partials;          // [2, grid, K]
+    unsigned int *bar;        // monotonic grid-barrier counter (zeroed before launch)
+    int64_t B;
+    int K, iters, rows_per_cta, scores_mode;
+    float inv_eps, r, c;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+template <int NV4>
+__global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
+    extern __shared__ float4 smem4[];
+    const int K = A.K, K4 = K >> 2;
+    float4 *E = smem4;                                                   // [rows_per_cta, K4]
+    float *a_s = reinterpret_cast<float *>(smem4 + (size_t)A.rows_per_cta * K4);    // [K]
+    float *red = a_s + K;                                                // [SKR_WARPS, K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_cta;
+    const int nrows = (int)max((int64_t)0, min((int64_t)A.rows_per_cta, A.B - row0));
+    unsigned int epoch = 0;
+
+    float4 acc[NV4];
+#pragma unroll
+    for (int v = 0; v < NV4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- pass 0: load, exponentiate, keep in shared memory, column sums
+    for (int rl = warp; rl < nrows; rl += SKR_WARPS) {
+        const float4 *src = reinterpret_cast<const float4 *>(A.in + (row0 + rl) * K);
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            if (i4 < K4) {
+                float4 e = __ldcs(src + i4);
+                if (A.scores_mode) {
+                    e.x = expf(e.x * A.inv_eps); e.y = expf(e.y * A.inv_eps);
+                    e.z = expf(e.z * A.inv_eps); e.w = expf(e.w * A.inv_eps);
+                }
+                E[(size_t)rl * K4 + i4] = e;
+                acc[v].x += e.x; acc[v].y += e.y; acc[v].z += e.z; acc[v].w += e.w;
+            }
+        }
+    }
+
+    for (int it = 0; it < A.iters; ++it) {
+        // ---- publish this CTA's marginal partial, grid barrier, fold all partials -> a_i = r / R_i
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            if (i4 < K4) reinterpret_cast<float4 *>(red + warp * K)[i4] = acc[v];
+        }
+        __syncthreads();
+        float *part = A.partials + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * K;
+        for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < SKR_WARPS; ++w) t += red[w * K + i];
+            part[i] = t;
+        }
+        grid_barrier(A.bar, (++epoch) * gridDim.x);
+        fold_partials<SKR_THREADS>(A.partials + (size_t)(it & 1) * gridDim.x * K, gridDim.x, K, red, a_s, A.r);
+        float4 av[NV4];
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            av[v] = (i4 < K4) ? reinterpret_cast<const float4 *>(a_s)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const bool last = (it == A.iters - 1);
+        // ---- sweep the resident rows: s_j = sum_i a_i E_ji ; then either R_i += E_ji * c/s_j or write Q
+        for (int rl = warp; rl < nrows; rl += SKR_WARPS) {
+            float4 e[NV4], p[NV4];
+            float s = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                const int i4 = lane + 32 * v;
+                e[v] = (i4 < K4) ? E[(size_t)rl * K4 + i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                p[v] = make_float4(e[v].x * av[v].x, e[v].y * av[v].y, e[v].z * av[v].z, e[v].w * av[v].w);
+                s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
+            }
+            s = warp_sum(s);
+            if (!last) {
+                const float b = __fdiv_rn(A.c, s);
+#pragma unroll
+                for (int v = 0; v < NV4; ++v) {
+                    acc[v].x = fmaf(e[v].x, b, acc[v].x); acc[v].y = fmaf(e[v].y, b, acc[v].y);
+                    acc[v].z = fmaf(e[v].z, b, acc[v].z); acc[v].w = fmaf(e[v].w, b, acc[v].w);
+                }
+            } else {
+                const float inv = __fdiv_rn(1.f, s);
+                float4 *dst = reinterpret_cast<float4 *>(A.q_out + (row0 + rl) * K);
+#pragma unroll
+                for (int v = 0; v < NV4; ++v) {
+                    const int i4 = lane + 32 * v;
+                    if (i4 < K4) __stcs(dst + i4, make_float4(p[v].x * inv, p[v].y * inv, p[v].z * inv, p[v].w * inv));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static bool sk_resident_plan(int64_t B, int K, int *grid, int *rows_per_cta, size_t *smem) {
+    if (K % 4 != 0 || K > 128 * SK_MAX_V4) return false;
+    const int g = num_sms();
+    const int64_t rpc = (B + g - 1) / g;
+    const size_t need = (size_t)rpc * K * 4 + (size_t)K * 4 + (size_t)SKR_WARPS * K * 4;
+    if (need > 220 * 1024) return false;
+    *grid = (int)((B + rpc - 1) / rpc);
+    *rows_per_cta = (int)rpc;
+    *smem = need;
+    return true;
+}
+
+template <int NV4>
+static int sk_resident_launch(SkResArgs &A, int grid, size_t smem, cudaStream_t st) {
+    TIMET_CUDA(cudaFuncSetAttribute(sk_resident<NV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {&A};
+    TIMET_CUDA(cudaLaunchCooperativeKernel((const void *)sk_resident<NV4>, dim3(grid), dim3(SKR_THREADS), args, smem, st));
+    launch_counter()++;
+    return TIMET_OK;
 }
 
 static int sk_grid(int64_t B) {
@@ -235,7 +401,7 @@ static int sk_launch(const SkArgs &A, int grid, cudaStream_t st) {
             default: sk_pass_vec<MODE, 4><<<grid, SK_THREADS, smem, st>>>(A); break;
         }
     } else {
-        const size_t smem = (size_t)2 * K * sizeof(float);
+        const size_t smem = (size_t)9 * K * sizeof(float);   // a_s[K] | red[K] (+ 8*K fold scratch starting at red)
         if (smem > 48 * 1024) {
             set_error("sinkhorn: K=%d too large for the scalar path", K);
             return TIMET_ERR_UNSUPPORTED;
@@ -276,6 +442,28 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
         return TIMET_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    {   // single GPU, >= 1 iteration, rows fit in shared memory: one cooperative launch
+        int rgrid, rpc;
+        size_t rsmem;
+        const char *force = getenv("TIMET_SK_STREAMING");
+        if (world_size == 1 && iters >= 1 && !(force && force[0] == '1') && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160) {
+            float *partials = (float *)workspace;
+            unsigned int *bar = (unsigned int *)(partials + (size_t)322 * K);
+            TIMET_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+            SkResArgs R;
+            R.in = in; R.q_out = q_out; R.partials = partials; R.bar = bar; R.B = B; R.K = K; R.iters = iters;
+            R.rows_per_cta = rpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
+            R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
+            R.r = 1.0f / (float)K; R.c = 1.0f / ((float)B * (float)world_size);
+            switch ((K / 4 + 31) / 32) {
+                case 1: return sk_resident_launch<1>(R, rgrid, rsmem, st);
+                case 2: return sk_resident_launch<2>(R, rgrid, rsmem, st);
+                case 3: return sk_resident_launch<3>(R, rgrid, rsmem, st);
+                default: return sk_resident_launch<4>(R, rgrid, rsmem, st);
+            }
+        }
+    }
     const int grid = sk_grid(B);
     TIMET_CHECK_ARG(grid <= 320, "sinkhorn: grid %d exceeds the workspace layout", grid);
     float *partials = (float *)workspace;
