@@ -273,3 +273,22 @@ def test_davis_style_eval_config4_slice():
     _, taint, _ = ff_taint(7, 12, 7, sr, feats, O.nearest_resize(first.numpy().astype(np.float64), sr, sr)[0])
     check_soft(out, ref, taint, what="davis-style")
     check_hard(out.argmax(1), ref, taint, what="davis-style hard")
+
+
+def test_host_pipeline_matches_device_step():
+    """The chunked host-fed pipeline (bench.py e2e path) gives bit-identical results to the device-resident step."""
+    from timetuning_b200.step import HostStepPipeline, ff_sinkhorn_step
+    bs, fs, sr, D, K = 4, 4, 14, 384, 200
+    N = sr * sr
+    backbone = synth.clip_features(bs, fs, sr, D, seed=1)
+    head = synth.head_features(backbone[:, [0, -1]], 256, seed=2)
+    protos = cu(synth.prototypes(K, 256, seed=3))
+    hs, ht = np.ascontiguousarray(head[:, 0]), np.ascontiguousarray(head[:, 1])
+    q1, t1, h1, _ = ff_sinkhorn_step(cu(hs), cu(ht), cu(backbone), protos)
+    pipe = HostStepPipeline(bs, fs, N, D, 256, K, chunks=2)
+    pin = [torch.from_numpy(x).pin_memory() for x in (hs, ht, backbone)]
+    for _ in range(2):
+        q2, t2, h2 = pipe.run(pin[0], pin[1], pin[2], protos)
+    torch.cuda.synchronize()
+    assert torch.equal(q1, q2) and torch.equal(t1, t2)
+    assert torch.equal(h1.cpu(), h2)

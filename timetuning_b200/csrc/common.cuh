@@ -45,8 +45,8 @@ int64_t &launch_counter();
 int num_sms();
 
 // ------------------------------------------------------------------ FF workspace layout
-constexpr int FF_CAND_CAP = 32;     // nominated candidates per (query, epilogue group)
-constexpr int FF_CAND_LISTS = 2;    // epilogue groups per query tile
+constexpr int FF_CAND_CAP = 32;     // in-kernel candidate list capacity per (query, epilogue group)
+constexpr int FF_CAND_STORE = 16;   // candidates published per query after the merged final compaction
 constexpr int FF_LIST_SLOTS = 32;   // in-register sorted list = one warp
 
 struct FFLayout {
@@ -74,8 +74,8 @@ static inline FFLayout ff_layout(const timet_ff_params &p) {
     L.off_sel_w = o; o = align_up(o + (size_t)L.queries * L.kw * sizeof(float), 1024);
     L.off_sel_k = o; o = align_up(o + (size_t)L.queries * L.kw * sizeof(int32_t), 1024);
     L.off_sel_cnt = o; o = align_up(o + (size_t)L.queries * sizeof(int32_t), 1024);
-    L.off_cand = o; o = align_up(o + (size_t)L.queries * FF_CAND_LISTS * FF_CAND_CAP * sizeof(uint32_t), 1024);
-    L.off_cand_meta = o; o = align_up(o + (size_t)L.queries * FF_CAND_LISTS * sizeof(uint32_t), 1024);
+    L.off_cand = o; o = align_up(o + (size_t)L.queries * FF_CAND_STORE * sizeof(uint32_t), 1024);
+    L.off_cand_meta = o; o = align_up(o + (size_t)L.queries * sizeof(uint32_t), 1024);
     L.off_stats = o; o = align_up(o + 8 * sizeof(int64_t), 1024);
     L.off_redo = o; o = align_up(o + 256 + (size_t)L.queries * sizeof(int32_t), 1024);   // count header + query ids
     L.total = o;

@@ -53,6 +53,7 @@ struct TcGeom {
 struct __align__(8) TcSmemCtl {
     uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
+    uint32_t xchg[128];       // group 1 -> group 0: cnt | lost << 16 per query
 };
 
 __device__ __forceinline__ float tc_decode(uint32_t entry) { return (float)(entry >> 13) * (1.0f / 131072.0f) - 2.0f; }
@@ -309,21 +310,34 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[g]);
         }
 
-        // ---- publish the candidate list of (query, group)
-        if (!DUMP) tc_compact(list, cnt, thr, lost, G.topk);
-        if (valid && tile_override < 0) {
-            const int64_t q = ((int64_t)clip * G.nT + (t - G.t_begin)) * G.N + qr0 * G.W + qi;
-            uint32_t *dst = cand + (q * FF_CAND_LISTS + g) * TC_CAP;
+        // ---- merge the two groups' lists per query, final compaction, publish <= FF_CAND_STORE candidates
+        if (!DUMP) {
+            tc_compact(list, cnt, thr, lost, G.topk);                  // cnt <= 16 in each list
+            if (g == 1) ctl->xchg[qi] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps
+            if (g == 0) {
+                const uint32_t other = ctl->xchg[qi];
+                const int cnt1 = (int)(other & 0xFFFFu);
+                lost |= (int)(other >> 16);
+                const uint32_t list1 = list + (uint32_t)TC_CAP * 128u * 4u;
+                for (int s = 0; s < cnt1; ++s) sts_u32(list + (uint32_t)(cnt + s) * TC_SLOT_STRIDE, lds_u32(list1 + s * TC_SLOT_STRIDE));
+                cnt += cnt1;                                            // <= 32 = list capacity
+                tc_compact(list, cnt, thr, lost, G.topk);              // joint k-th - slack; cnt <= 16
+                if (valid && tile_override < 0) {
+                    const int64_t q = ((int64_t)clip * G.nT + (t - G.t_begin)) * G.N + qr0 * G.W + qi;
+                    uint32_t *dst = cand + q * FF_CAND_STORE;
 #pragma unroll
-            for (int s4 = 0; s4 < TC_CAP / 2; s4 += 4) {
-                if (s4 < cnt) {
-                    uint4 v;
-                    v.x = lds_u32(list + (s4 + 0) * TC_SLOT_STRIDE); v.y = lds_u32(list + (s4 + 1) * TC_SLOT_STRIDE);
-                    v.z = lds_u32(list + (s4 + 2) * TC_SLOT_STRIDE); v.w = lds_u32(list + (s4 + 3) * TC_SLOT_STRIDE);
-                    *reinterpret_cast<uint4 *>(dst + s4) = v;
+                    for (int s4 = 0; s4 < FF_CAND_STORE; s4 += 4) {
+                        if (s4 < cnt) {
+                            uint4 v;
+                            v.x = lds_u32(list + (s4 + 0) * TC_SLOT_STRIDE); v.y = lds_u32(list + (s4 + 1) * TC_SLOT_STRIDE);
+                            v.z = lds_u32(list + (s4 + 2) * TC_SLOT_STRIDE); v.w = lds_u32(list + (s4 + 3) * TC_SLOT_STRIDE);
+                            *reinterpret_cast<uint4 *>(dst + s4) = v;
+                        }
+                    }
+                    cand_meta[q] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
                 }
             }
-            cand_meta[q * FF_CAND_LISTS + g] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
         }
     }
 
@@ -339,6 +353,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 // ------------------------------------------------------------------ finalize: exact re-evaluation
 // One warp per query: lane-per-candidate canonical fp32 dot, exp, reference selection with ties.
 constexpr int FIN_WARPS = 8;
+constexpr int FIN_QPB = 64;                    // consecutive queries per CTA
 
 __global__ void __launch_bounds__(FIN_WARPS * 32)
 ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float *__restrict__ fn32,
@@ -354,11 +369,12 @@ ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float
     float4 *qs = qsm + (size_t)warp * (Dp >> 2);
     const int W = p.grid_w;
     unsigned long long st_sel = 0, st_ties = 0, st_trunc = 0, st_cand = 0;
-    const int64_t nwarps = (int64_t)gridDim.x * FIN_WARPS;
-    for (int64_t qid = (int64_t)blockIdx.x * FIN_WARPS + warp; qid < n_queries; qid += nwarps) {
-        const uint32_t m0 = cand_meta[qid * 2 + 0], m1 = cand_meta[qid * 2 + 1];
-        const int c0 = (int)(m0 & 0xFFFFu), c1 = (int)(m1 & 0xFFFFu);
-        if (((m0 | m1) & 0x10000u) != 0u) {
+    // each CTA sweeps FIN_QPB consecutive queries (8 at a time): neighbouring queries nominate overlapping
+    // keys, so their fp32 rows are served from L1 instead of L2
+    for (int64_t qid = (int64_t)blockIdx.x * FIN_QPB + warp; qid < min(n_queries, ((int64_t)blockIdx.x + 1) * FIN_QPB); qid += FIN_WARPS) {
+        const uint32_t m0 = cand_meta[qid];
+        const int nc = (int)(m0 & 0xFFFFu);
+        if ((m0 & 0x10000u) != 0u) {
             if (lane == 0) redo_list[atomicAdd(redo_count, 1u)] = (int32_t)qid;
             continue;
         }
@@ -372,13 +388,11 @@ ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float
         for (int d = lane; d < (Dp >> 2); d += 32) qs[d] = qrow[d];
         __syncwarp();
         const int qr = i / W, qc = i - qr * W;
-        // lane j owns candidate j of the concatenated lists (c0 + c1 <= 32)
-        const int nc = c0 + c1;
+        // lane j owns candidate j (nc <= FF_CAND_STORE)
         const bool has = lane < nc;
         int32_t key = 0, krow = 0;
         if (has) {
-            const uint32_t code = (lane < c0 ? cand[(qid * 2 + 0) * TC_CAP + lane]
-                                             : cand[(qid * 2 + 1) * TC_CAP + (lane - c0)]) & 0x1FFFu;
+            const uint32_t code = cand[qid * FF_CAND_STORE + lane] & 0x1FFFu;
             const int ci = (int)(code >> 10), wr = (int)((code >> 5) & 31u), wc = (int)(code & 31u);
             const int f = ctx_frame(t, p.n_last_frames, ci);
             const int j = (qr - p.radius + wr) * W + (qc - p.radius + wc);
@@ -399,7 +413,7 @@ ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float
         st_sel += (unsigned long long)(m < kw ? m : kw);
         st_ties += (m > p.topk);
         st_trunc += (m > kw);
-        st_cand += (unsigned long long)(c0 + c1);
+        st_cand += (unsigned long long)nc;
     }
     if (lane == 0) {
         atomicAdd(&s_stat[0], st_sel);
@@ -516,10 +530,8 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
     unsigned int *redo_count = reinterpret_cast<unsigned int *>(ws + L.off_redo);
     int32_t *redo_list = reinterpret_cast<int32_t *>(ws + L.off_redo + 256);
     const size_t fsmem = (size_t)FIN_WARPS * L.Dp * sizeof(float);
-    int64_t blocks = (L.queries + FIN_WARPS - 1) / FIN_WARPS;
-    const int64_t cap = (int64_t)num_sms() * 8;
-    if (blocks > cap) blocks = cap;
-    ff_finalize_kernel<<<(int)blocks, FIN_WARPS * 32, fsmem, st>>>(
+    const int64_t blocks = (L.queries + FIN_QPB - 1) / FIN_QPB;
+    ff_finalize_kernel<<<(unsigned)blocks, FIN_WARPS * 32, fsmem, st>>>(
         p, L.N, L.Dp, L.nT, L.kw, reinterpret_cast<const float *>(ws + L.off_fn32), cand, meta,
         reinterpret_cast<float *>(ws + L.off_sel_w), reinterpret_cast<int32_t *>(ws + L.off_sel_k),
         reinterpret_cast<int32_t *>(ws + L.off_sel_cnt), reinterpret_cast<unsigned long long *>(ws + L.off_stats),
