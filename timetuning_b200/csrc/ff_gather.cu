@@ -29,47 +29,86 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
 }
 
 constexpr int GA_THREADS = 512;
+constexpr int GA_WARPS = GA_THREADS / 32;
 
-template <bool VEC>
-__global__ void __launch_bounds__(GA_THREADS)
+template <typename V>
+__device__ __forceinline__ V ga_zero();
+template <>
+__device__ __forceinline__ float ga_zero<float>() { return 0.f; }
+template <>
+__device__ __forceinline__ float4 ga_zero<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void ga_fma(float &a, float w, float l) { a = fmaf(w, l, a); }
+__device__ __forceinline__ void ga_fma(float4 &a, float w, const float4 l) {
+    a.x = fmaf(w, l.x, a.x); a.y = fmaf(w, l.y, a.y); a.z = fmaf(w, l.z, a.z); a.w = fmaf(w, l.w, a.w);
+}
+
+// V = float4 (C % 4 == 0) or float.  One WARP per query: lane m holds (weight, key) m of the sparse row,
+// broadcast by shuffle; every lane then owns channel vectors c = lane, lane+32, ... and issues the <= 4 gathered
+// row loads of a batch back to back (coherent L2 loads: earlier frames were written by other CTAs of this
+// launch).  The next query's sparse row is prefetched while the current one is gathered.
+template <typename V>
+__global__ void __launch_bounds__(GA_THREADS, 2)
 ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const float *__restrict__ sel_w,
                  const int32_t *__restrict__ sel_k, const int32_t *__restrict__ sel_cnt, int n_frames, int N, int C,
                  int nT, int kw, int t_begin) {
     const unsigned cs = cluster_nctarank(), cr = cluster_ctarank();
     const int clip = blockIdx.x / cs;
-    const int CV = VEC ? (C >> 2) : C;
-    const int items = N * CV;
+    constexpr int VW = sizeof(V) / sizeof(float);
+    const int CV = C / VW;
+    const int lane = threadIdx.x & 31;
+    const int wid = cr * GA_WARPS + (threadIdx.x >> 5), nw = cs * GA_WARPS;
     float *clip_base = labels + (int64_t)clip * n_frames * N * C;
     for (int t = t_begin; t < n_frames; ++t) {
         const int64_t q0 = ((int64_t)clip * nT + (t - t_begin)) * N;
-        for (int idx = cr * GA_THREADS + threadIdx.x; idx < items; idx += cs * GA_THREADS) {
-            const int i = idx / CV, c = idx - i * CV;
-            const int64_t q = q0 + i;
-            const int cnt = __ldg(sel_cnt + q);
-            const float *w = sel_w + q * kw;
-            const int32_t *kk = sel_k + q * kw;
-            if (VEC) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int m = 0; m < cnt; ++m) {
-                    const float wm = __ldg(w + m);
-                    // labels of earlier frames were written in this kernel by other CTAs: coherent (L2) loads
-                    const float4 l = __ldcg(reinterpret_cast<const float4 *>(clip_base + (int64_t)__ldg(kk + m) * C) + c);
-                    acc.x = fmaf(wm, l.x, acc.x); acc.y = fmaf(wm, l.y, acc.y);
-                    acc.z = fmaf(wm, l.z, acc.z); acc.w = fmaf(wm, l.w, acc.w);
-                }
-                *(reinterpret_cast<float4 *>(clip_base + ((int64_t)t * N + i) * C) + c) = acc;
-            } else {
-                float acc = 0.f;
-                for (int m = 0; m < cnt; ++m) acc = fmaf(__ldg(w + m), __ldcg(clip_base + (int64_t)__ldg(kk + m) * C + c), acc);
-                clip_base[((int64_t)t * N + i) * C + c] = acc;
+        int i = wid;
+        int cnt = 0;
+        float w_l = 0.f;
+        int32_t k_l = 0;
+        if (i < N) {
+            cnt = __ldg(sel_cnt + q0 + i);
+            if (lane < kw) { w_l = __ldg(sel_w + (q0 + i) * kw + lane); k_l = __ldg(sel_k + (q0 + i) * kw + lane); }
+        }
+        while (i < N) {
+            const int inext = i + nw;
+            int cnt_n = 0;
+            float w_n = 0.f;
+            int32_t k_n = 0;
+            if (inext < N) {   // prefetch the next sparse row
+                cnt_n = __ldg(sel_cnt + q0 + inext);
+                if (lane < kw) { w_n = __ldg(sel_w + (q0 + inext) * kw + lane); k_n = __ldg(sel_k + (q0 + inext) * kw + lane); }
             }
+            V *dst = reinterpret_cast<V *>(clip_base + ((int64_t)t * N + i) * C);
+            for (int c0 = 0; c0 < CV; c0 += 64) {          // warp-uniform: the shuffles below need every lane
+                const int c = c0 + lane, c2 = c + 32;
+                const bool one = c < CV, two = c2 < CV;
+                V acc0 = ga_zero<V>(), acc1 = ga_zero<V>();
+                for (int m0 = 0; m0 < cnt; m0 += 4) {
+                    float wm[4];
+                    V l0[4], l1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int m = min(m0 + u, 31);
+                        wm[u] = __shfl_sync(0xffffffffu, w_l, m);
+                        const int32_t km = __shfl_sync(0xffffffffu, k_l, m);
+                        const V *row = reinterpret_cast<const V *>(clip_base + (int64_t)km * C);
+                        const bool on = m0 + u < cnt;
+                        l0[u] = (on && one) ? __ldcg(row + c) : ga_zero<V>();
+                        l1[u] = (on && two) ? __ldcg(row + c2) : ga_zero<V>();
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (m0 + u < cnt) { ga_fma(acc0, wm[u], l0[u]); ga_fma(acc1, wm[u], l1[u]); }
+                    }
+                }
+                if (one) dst[c] = acc0;
+                if (two) dst[c2] = acc1;
+            }
+            i = inext; cnt = cnt_n; w_l = w_n; k_l = k_n;
         }
         cluster_barrier();
     }
     if (hard) {   // argmax over channels of the last frame, lowest index on ties (time_tuning.py:296)
-        const int lane = threadIdx.x & 31;
-        const int warps = cs * (GA_THREADS >> 5);
-        for (int i = cr * (GA_THREADS >> 5) + (threadIdx.x >> 5); i < N; i += warps) {
+        for (int i = wid; i < N; i += nw) {
             const float *row = clip_base + ((int64_t)(n_frames - 1) * N + i) * C;
             float best = -INFINITY;
             int bi = 0x7fffffff;
@@ -93,10 +132,9 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
     const int32_t *sel_k = reinterpret_cast<const int32_t *>(ws + L.off_sel_k);
     const int32_t *sel_cnt = reinterpret_cast<const int32_t *>(ws + L.off_sel_cnt);
     const bool vec = (p.n_channels % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0);
-    const int CV = vec ? p.n_channels / 4 : p.n_channels;
     // cluster size: as many CTAs per clip as useful (<= 8, power of two) without exceeding ~2 CTAs per SM in total
     int cs = 8;
-    while (cs > 1 && ((int64_t)p.n_clips * cs > 2 * (int64_t)num_sms() || (int64_t)L.N * CV < (int64_t)cs * GA_THREADS / 2)) cs >>= 1;
+    while (cs > 1 && ((int64_t)p.n_clips * cs > 2 * (int64_t)num_sms() || (int64_t)L.N < (int64_t)cs * GA_WARPS)) cs >>= 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(p.n_clips * cs));
     cfg.blockDim = dim3(GA_THREADS);
@@ -110,10 +148,10 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (vec)
-        TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<true>, labels, hard, sel_w, sel_k, sel_cnt, (int)p.n_frames,
+        TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4>, labels, hard, sel_w, sel_k, sel_cnt, (int)p.n_frames,
                                       L.N, (int)p.n_channels, L.nT, L.kw, (int)p.t_begin));
     else
-        TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<false>, labels, hard, sel_w, sel_k, sel_cnt, (int)p.n_frames,
+        TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float>, labels, hard, sel_w, sel_k, sel_cnt, (int)p.n_frames,
                                       L.N, (int)p.n_channels, L.nT, L.kw, (int)p.t_begin));
     TIMET_LAUNCHED();
     return TIMET_OK;

@@ -11,6 +11,19 @@
 
 namespace timet {
 
+constexpr int PREP_KEEP = 8;
+
+__device__ __forceinline__ void prep_store(float *d32, __half *d16, int i, float4 v, float denom) {
+    v.x = __fdiv_rn(v.x, denom); v.y = __fdiv_rn(v.y, denom);
+    v.z = __fdiv_rn(v.z, denom); v.w = __fdiv_rn(v.w, denom);
+    __stcs(reinterpret_cast<float4 *>(d32) + i, v);
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+    reinterpret_cast<uint2 *>(d16)[i] = pk;
+}
+
 __global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict__ feats, float *__restrict__ fn32,
                                                          __half *__restrict__ fn16, int64_t rows, int dim, int Dp) {
     const int lane = threadIdx.x & 31;
@@ -20,11 +33,24 @@ __global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict
     for (int64_t row = warp; row < rows; row += nwarps) {
         const float *src = feats + row * dim;
         float ss = 0.f;
+        float4 keep[PREP_KEEP];                       // the lane's slice of the row, read once (dim <= 1024)
+        const bool cached = vec && (dim >> 2) <= 32 * PREP_KEEP;
         if (vec) {
             const float4 *s4 = reinterpret_cast<const float4 *>(src);
-            for (int i = lane; i < (dim >> 2); i += 32) {
-                const float4 v = __ldcs(s4 + i);
-                ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            if (cached) {
+#pragma unroll
+                for (int u = 0; u < PREP_KEEP; ++u) {
+                    const int i = lane + 32 * u;
+                    keep[u] = (i < (dim >> 2)) ? __ldcs(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < PREP_KEEP; ++u)
+                    ss += (keep[u].x * keep[u].x + keep[u].y * keep[u].y) + (keep[u].z * keep[u].z + keep[u].w * keep[u].w);
+            } else {
+                for (int i = lane; i < (dim >> 2); i += 32) {
+                    const float4 v = s4[i];
+                    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                }
             }
         } else {
             for (int i = lane; i < dim; i += 32) { const float v = src[i]; ss = fmaf(v, v, ss); }
@@ -34,25 +60,26 @@ __global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict
         float *d32 = fn32 + row * Dp;
         __half *d16 = fn16 + row * Dp;
         // Dp % 64 == 0 -> float4 / half2x2 stores are aligned
-        for (int i = lane; i < (Dp >> 2); i += 32) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int d = i << 2;
-            if (vec) {
-                if (d < dim) v = reinterpret_cast<const float4 *>(src)[i];
-            } else {
-                if (d + 0 < dim) v.x = src[d + 0];
-                if (d + 1 < dim) v.y = src[d + 1];
-                if (d + 2 < dim) v.z = src[d + 2];
-                if (d + 3 < dim) v.w = src[d + 3];
+        if (cached) {
+#pragma unroll
+            for (int u = 0; u < PREP_KEEP; ++u) {
+                const int i = lane + 32 * u;
+                if (i < (Dp >> 2)) prep_store(d32, d16, i, keep[u], denom);     // keep[u] is zero past dim
             }
-            v.x = __fdiv_rn(v.x, denom); v.y = __fdiv_rn(v.y, denom);
-            v.z = __fdiv_rn(v.z, denom); v.w = __fdiv_rn(v.w, denom);
-            reinterpret_cast<float4 *>(d32)[i] = v;
-            const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-            reinterpret_cast<uint2 *>(d16)[i] = pk;
+        } else {
+            for (int i = lane; i < (Dp >> 2); i += 32) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int d = i << 2;
+                if (vec) {
+                    if (d < dim) v = reinterpret_cast<const float4 *>(src)[i];
+                } else {
+                    if (d + 0 < dim) v.x = src[d + 0];
+                    if (d + 1 < dim) v.y = src[d + 1];
+                    if (d + 2 < dim) v.z = src[d + 2];
+                    if (d + 3 < dim) v.w = src[d + 3];
+                }
+                prep_store(d32, d16, i, v, denom);
+            }
         }
     }
 }
