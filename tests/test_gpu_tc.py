@@ -2,6 +2,7 @@
 error bound the nomination relies on, and bit-exact agreement with the exact engine."""
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -17,7 +18,9 @@ FF_TC_DELTA = 1.05e-3
 
 def geometry(H, W, radius):
     q = 16 // math.gcd(W, 16)
-    RPC = (256 // W) // q * q
+    RPC = (256 // W) // q * q          # 2 TMEM buffers of 256 columns (default) ...
+    if os.environ.get("TIMET_TC_NBUF") == "4" and (128 // W) // q >= 1:
+        RPC = (128 // W) // q * q      # ... or 4 x 128
     QR = min(128 // W, H)
     return dict(QR=QR, tpf=-(-H // QR), RPC=RPC, NT=RPC * W, qrows=q)
 

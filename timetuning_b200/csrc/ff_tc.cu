@@ -31,8 +31,9 @@
 
 namespace timet {
 
-constexpr int TC_THREADS = 384;
-constexpr int TC_STAGES = 3;
+constexpr int TC_GROUPS = 4;                    // epilogue warpgroups (4 warps each)
+constexpr int TC_THREADS = 128 + TC_GROUPS * 128;
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_NKC = 6;                  // resident query tile: Dp <= 384
 constexpr int TC_CLIP_GROUP = 8;                // clips whose tiles are launched together (L2 locality)
 constexpr int TC_CAP = FF_CAND_CAP;            // 32 candidates per (query, epilogue group)
@@ -45,16 +46,22 @@ struct TcGeom {
     int QR, tiles_per_frame;
     int RPC, NT, qrows;
     int n_clips, n_frames, nT, t_begin, n_last, radius, topk;
+    int nbuf, buf_cols, nstages;   // TMEM accumulator buffers (4 x 128 or 2 x 256 columns), B ring depth
+    int cap;                       // candidate slots per (query, group): 16 (topk <= 5) or 32
     int trig;                 // compaction trigger
     int flags;                // debug (env TIMET_TC_FLAGS): 1 = epilogue releases tiles unscanned, 2 = scan but never append
     int64_t total_tiles;
 };
 
 struct __align__(8) TcSmemCtl {
-    uint64_t full[TC_STAGES], empty[TC_STAGES], a_full, tmem_full[2], tmem_empty[2];
+    uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], a_full, tmem_full[4], tmem_empty[4];
     uint32_t tmem_base;
-    uint32_t xchg[128];       // group 1 -> group 0: cnt | lost << 16 per query
+    uint32_t thr_sh[128];     // per-query nomination threshold shared by the groups: float bits of (thr + 4), atomicMax
+    uint32_t xchg[3][128];    // groups 1..3 -> group 0: cnt | lost << 16 per query
 };
+
+__device__ __forceinline__ uint32_t thr_enc(float thr) { return __float_as_uint(fmaxf(thr, -3.0f) + 4.0f); }
+__device__ __forceinline__ float thr_dec(uint32_t v) { return __uint_as_float(v) - 4.0f; }
 
 __device__ __forceinline__ float tc_decode(uint32_t entry) { return (float)(entry >> 13) * (1.0f / 131072.0f) - 2.0f; }
 
@@ -90,8 +97,8 @@ __device__ __forceinline__ void tc_offer(uint32_t &slot_addr, float v, float thr
 // Raise thr from the list content and drop entries that can no longer be among the top-k.
 // One pass over the list keeps the 8 largest packed entries in sorted registers (max/min chain), so the
 // k-th largest (k <= 8) is read off directly.  Warp-synchronous; loop bounds are warp-uniform.
-// Afterwards cnt <= TC_CAP/2 (entries beyond that are dropped and the query is flagged for the exact re-do).
-__device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, int &lost, int k) {
+// Afterwards cnt <= keep_max (entries beyond that are dropped and the query is flagged for the exact re-do).
+__device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, int &lost, int k, int keep_max) {
     int maxcnt = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
@@ -122,8 +129,23 @@ __device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, 
         if (s < cnt && e >= enc) { sts_u32(dst, e); dst += TC_SLOT_STRIDE; }
     }
     int j = (int)((dst - list) / TC_SLOT_STRIDE);
-    if (j > TC_CAP / 2) { j = TC_CAP / 2; lost = 1; }
+    if (j > keep_max) { j = keep_max; lost = 1; }
     cnt = j;
+}
+
+// Drop entries below thr (no k-th search).  Warp-synchronous.
+__device__ __forceinline__ void tc_filter(uint32_t list, int &cnt, float thr) {
+    int maxcnt = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
+    const float lim = (thr + 2.0f) * 131072.0f;
+    const uint32_t enc = (lim <= 0.f) ? 0u : ((uint32_t)lim << 13);
+    uint32_t dst = list;
+    for (int s = 0; s < maxcnt; ++s) {
+        const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
+        if (s < cnt && e >= enc) { sts_u32(dst, e); dst += TC_SLOT_STRIDE; }
+    }
+    cnt = (int)((dst - list) / TC_SLOT_STRIDE);
 }
 
 template <bool DUMP>
@@ -132,13 +154,13 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
              uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, int64_t tile_override,
              float *__restrict__ dump) {
     extern __shared__ uint8_t smem_raw[];
-    // carve: [A: NKC x 16 KB][B: TC_STAGES x NT*128][lists: 2 x 32 x 128 u32][ctl]; 1024-aligned for SWIZZLE_128B
+    // carve: [A: NKC x 16 KB][B: nstages x NT*128][lists: 4 x 32 x 128 u32][ctl]; 1024-aligned for SWIZZLE_128B
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     const uint32_t b_stage_bytes = (uint32_t)G.NT * 128u;
     uint8_t *sB = sA + (size_t)G.NKC * 16384;
-    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)TC_STAGES * b_stage_bytes);
-    TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(sList + 2 * TC_CAP * 128);
+    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * b_stage_bytes);
+    TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(sList + TC_GROUPS * G.cap * 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -171,12 +193,14 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         ptx::prefetch_tensormap(&map_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
+        for (int s = 0; s < G.nstages; ++s) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
         ptx::mbar_init(&ctl->a_full, 1);
-        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctl->tmem_full[b], 1); ptx::mbar_init(&ctl->tmem_empty[b], 4); }
+        // every warp that reads a buffer arrives once per tile: 4 warps (one group) or 8 (two groups splitting the rows)
+        for (int b = 0; b < G.nbuf; ++b) { ptx::mbar_init(&ctl->tmem_full[b], 1); ptx::mbar_init(&ctl->tmem_empty[b], G.nbuf == 4 ? 4 : 8); }
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc<512>(&ctl->tmem_base);
+    if (warp == 3) for (int i = lane; i < 128; i += 32) ctl->thr_sh[i] = thr_enc(-INFINITY);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -193,8 +217,8 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const int k_row0 = (int)(clip_row0 + (int64_t)f * G.N + (kr_lo + ch * G.RPC) * G.W);
                     for (int kc = 0; kc < G.NKC; ++kc, ++it) {
-                        const int stage = it % TC_STAGES;
-                        const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                        const int stage = it % G.nstages;
+                        const uint32_t ph = (uint32_t)(it / G.nstages) & 1u;
                         ptx::mbar_wait(&ctl->empty[stage], ph ^ 1u);
                         ptx::mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
                         ptx::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, kc * 64, k_row0, &ctl->full[stage]);
@@ -215,14 +239,14 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 const int rc = min(G.RPC, rows_left);
                 const int n_mma = min(G.NT, (rc + G.qrows - 1) / G.qrows * G.qrows * G.W);
                 const uint32_t idesc = ptx::umma_idesc_f16(128, n_mma);
-                const int buf = tile & 1;
-                const uint32_t use = (uint32_t)(tile >> 1);
+                const int buf = tile % G.nbuf;
+                const uint32_t use = (uint32_t)(tile / G.nbuf);
                 ptx::mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G.buf_cols);
                 for (int kc = 0; kc < G.NKC; ++kc, ++it) {
-                    const int stage = it % TC_STAGES;
-                    const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                    const int stage = it % G.nstages;
+                    const uint32_t ph = (uint32_t)(it / G.nstages) & 1u;
                     ptx::mbar_wait(&ctl->full[stage], ph);
                     ptx::tc_fence_after();
 #pragma unroll
@@ -238,10 +262,15 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // =========================== epilogue groups ===========================
-        const int g = (warp - 4) >> 2;                              // 0: even key tiles, 1: odd key tiles
+        // 4 buffers: group g owns key tiles g, g+4, ...   2 buffers: groups g and g+2 share the tiles of buffer
+        // g & 1 and split their key rows by parity.
+        const int g = (warp - 4) >> 2;
+        const int buf = (G.nbuf == 4) ? g : (g & 1);
+        const int row_par = (G.nbuf == 4) ? -1 : (g >> 1);
         const int qi = ((warp & 3) << 5) + lane;                    // TMEM lane == query row of the tile
         const uint32_t lane_base = (uint32_t)((warp & 3) << 5) << 16;
-        const uint32_t list = ptx::smem_u32(sList + (size_t)g * TC_CAP * 128 + qi);   // slot s at list + s * 512 B
+        const uint32_t list = ptx::smem_u32(sList + (size_t)g * G.cap * 128 + qi);   // slot s at list + s * 512 B
+        const int half = G.cap >> 1;                                  // max entries kept across a compaction
         const bool valid = qi < nq;
         const int qrow = qr0 + qi / G.W, qcol = qi % G.W;
         const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
@@ -250,79 +279,98 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         float thr = (G.flags & 2) ? INFINITY : -INFINITY;
         int cnt = 0, lost = 0;
 
-        for (int tile = g; tile < ntiles; tile += 2) {
+        for (int tile = buf; tile < ntiles; tile += G.nbuf) {
             const int ci = tile / nchunks, ch = tile - ci * nchunks;
             const int kr_start = kr_lo + ch * G.RPC;
             const int rc = min(G.RPC, kr_hi + 1 - kr_start);
-            const uint32_t use = (uint32_t)(tile >> 1);
-            ptx::mbar_wait(&ctl->tmem_full[g], use & 1u);
+            const uint32_t use = (uint32_t)(tile / G.nbuf);
+            ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u);
             ptx::tc_fence_after();
-            const uint32_t t_acc = tmem_base + (uint32_t)g * 256u + lane_base;
+            const uint32_t t_acc = tmem_base + (uint32_t)(buf * G.buf_cols) + lane_base;
+            thr = fmaxf(thr, thr_dec(ctl->thr_sh[qi]));               // what the other groups have established
 
-            if (DUMP) {
-                for (int c0 = 0; c0 < 256; c0 += 32) {
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(t_acc + c0, r);
+            if (DUMP && row_par <= 0) {
+                for (int c0 = 0; c0 < G.buf_cols; c0 += 16) {
+                    uint32_t r[16];
+                    ptx::tmem_ld_32x16(t_acc + c0, r);
                     ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) dump[((size_t)tile * 128 + qi) * 256 + c0 + e] = __uint_as_float(r[e]);
+                    for (int e = 0; e < 16; ++e) dump[((size_t)tile * 128 + qi) * 256 + c0 + e] = __uint_as_float(r[e]);
                 }
             }
 
             for (int rr = 0; rr < ((G.flags & 1) ? 0 : rc); ++rr) {
+                if (row_par >= 0 && (rr & 1) != row_par) continue;
                 const int kr = kr_start + rr;
                 const bool row_ok = valid && kr >= r_lo && kr <= r_hi;
                 if (!__any_sync(0xffffffffu, row_ok)) continue;
                 const int code_row = (ci << 10) | ((kr - r_lo) << 5);
-                for (int cb = 0; cb < G.W; cb += 32) {
+                for (int cb = 0; cb < G.W; cb += 16) {
                     int col0 = rr * G.W + cb;
-                    const int shift = max(0, col0 + 32 - 256);      // keep the 32-column load inside the buffer
+                    const int shift = max(0, col0 + 16 - G.buf_cols);   // keep the 16-column load inside the buffer
                     col0 -= shift;
-                    const int cb_eff = cb - shift;                  // register e holds key column cb_eff + e
-                    uint32_t r[32];
-                    ptx::tmem_ld_32x32(t_acc + (uint32_t)col0, r);
+                    const int cb_eff = cb - shift;                      // register e holds key column cb_eff + e
+                    uint32_t r[16];
+                    ptx::tmem_ld_32x16(t_acc + (uint32_t)col0, r);
                     // window columns of this thread inside the block -> bit mask over e
-                    const int lo = max(c_lo_cl - cb_eff, shift), hi = min(c_hi_cl - cb_eff, 31);
+                    const int lo = max(c_lo_cl - cb_eff, shift), hi = min(c_hi_cl - cb_eff, 15);
                     uint32_t wmask = 0u;
-                    if (row_ok && hi >= lo) wmask = (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo);
+                    if (row_ok && hi >= lo) wmask = (0xFFFFu >> (15 - hi)) & (0xFFFFu << lo) & 0xFFFFu;
                     const uint32_t code0 = (uint32_t)(code_row + (cb_eff - c_lo));
                     uint32_t slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
                     ptx::tmem_ld_wait();
-                    // invariant: cnt <= 16 here, and each half appends at most 16 -> the 32 slots cannot overflow
 #define TC_OFFER(E) tc_offer<(1u << (E))>(slot, __uint_as_float(r[E]), thr, wmask, code0 + (E));
+                    // invariant: cnt <= cap/2 before every run of cap/2 offers -> the cap slots cannot overflow
                     TC_OFFER(0) TC_OFFER(1) TC_OFFER(2) TC_OFFER(3) TC_OFFER(4) TC_OFFER(5) TC_OFFER(6) TC_OFFER(7)
-                    TC_OFFER(8) TC_OFFER(9) TC_OFFER(10) TC_OFFER(11) TC_OFFER(12) TC_OFFER(13) TC_OFFER(14) TC_OFFER(15)
-                    cnt = (int)((slot - list) / TC_SLOT_STRIDE);
-                    if (__any_sync(0xffffffffu, cnt > TC_CAP / 2)) {
-                        tc_compact(list, cnt, thr, lost, G.topk);
-                        slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
+                    if (G.cap == 16) {
+                        cnt = (int)((slot - list) / TC_SLOT_STRIDE);
+                        if (__any_sync(0xffffffffu, cnt > half)) {
+                            const float before = thr;
+                            tc_compact(list, cnt, thr, lost, G.topk, half);
+                            if (thr > before) atomicMax(&ctl->thr_sh[qi], thr_enc(thr));
+                            slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
+                        }
                     }
-                    TC_OFFER(16) TC_OFFER(17) TC_OFFER(18) TC_OFFER(19) TC_OFFER(20) TC_OFFER(21) TC_OFFER(22) TC_OFFER(23)
-                    TC_OFFER(24) TC_OFFER(25) TC_OFFER(26) TC_OFFER(27) TC_OFFER(28) TC_OFFER(29) TC_OFFER(30) TC_OFFER(31)
+                    TC_OFFER(8) TC_OFFER(9) TC_OFFER(10) TC_OFFER(11) TC_OFFER(12) TC_OFFER(13) TC_OFFER(14) TC_OFFER(15)
 #undef TC_OFFER
                     cnt = (int)((slot - list) / TC_SLOT_STRIDE);
-                    if (__any_sync(0xffffffffu, cnt > TC_CAP / 2)) tc_compact(list, cnt, thr, lost, G.topk);
+                    if (__any_sync(0xffffffffu, cnt > half)) {
+                        const float before = thr;
+                        tc_compact(list, cnt, thr, lost, G.topk, half);
+                        if (thr > before) atomicMax(&ctl->thr_sh[qi], thr_enc(thr));
+                    }
                 }
             }
             // release the accumulator buffer to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[g]);
+            if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
         }
 
-        // ---- merge the two groups' lists per query, final compaction, publish <= FF_CAND_STORE candidates
+        // ---- final: agree on the per-query threshold, filter, merge the 4 lists, publish <= FF_CAND_STORE candidates
         if (!DUMP) {
-            tc_compact(list, cnt, thr, lost, G.topk);                  // cnt <= 16 in each list
-            if (g == 1) ctl->xchg[qi] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
-            asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps
+            {
+                const float before = thr;
+                tc_compact(list, cnt, thr, lost, G.topk, half);
+                if (thr > before) atomicMax(&ctl->thr_sh[qi], thr_enc(thr));
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");            // the 16 epilogue warps
+            thr = fmaxf(thr, thr_dec(ctl->thr_sh[qi]));
+            tc_filter(list, cnt, thr);
+            if (g > 0) ctl->xchg[g - 1][qi] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             if (g == 0) {
-                const uint32_t other = ctl->xchg[qi];
-                const int cnt1 = (int)(other & 0xFFFFu);
-                lost |= (int)(other >> 16);
-                const uint32_t list1 = list + (uint32_t)TC_CAP * 128u * 4u;
-                for (int s = 0; s < cnt1; ++s) sts_u32(list + (uint32_t)(cnt + s) * TC_SLOT_STRIDE, lds_u32(list1 + s * TC_SLOT_STRIDE));
-                cnt += cnt1;                                            // <= 32 = list capacity
-                tc_compact(list, cnt, thr, lost, G.topk);              // joint k-th - slack; cnt <= 16
+                for (int og = 1; og < TC_GROUPS; ++og) {
+                    const uint32_t other = ctl->xchg[og - 1][qi];
+                    const int ocnt = (int)(other & 0xFFFFu);
+                    lost |= (int)(other >> 16);
+                    const uint32_t olist = list + (uint32_t)og * (uint32_t)G.cap * 128u * 4u;
+                    for (int s = 0; s < ocnt; ++s) {
+                        if (cnt < G.cap) { sts_u32(list + (uint32_t)cnt * TC_SLOT_STRIDE, lds_u32(olist + s * TC_SLOT_STRIDE)); ++cnt; }
+                        else lost = 1;
+                    }
+                }
+                tc_compact(list, cnt, thr, lost, G.topk, min(G.cap, FF_CAND_STORE));   // joint k-th - slack
                 if (valid && tile_override < 0) {
                     const int64_t q = ((int64_t)clip * G.nT + (t - G.t_begin)) * G.N + qr0 * G.W + qi;
                     uint32_t *dst = cand + q * FF_CAND_STORE;
@@ -471,6 +519,10 @@ static int make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int 
     return TIMET_OK;
 }
 
+static size_t tc_smem_bytes(const TcGeom &G) {
+    return 1024 + (size_t)G.NKC * 16384 + (size_t)G.nstages * G.NT * 128 + (size_t)TC_GROUPS * G.cap * 128 * 4 + sizeof(TcSmemCtl) + 64;
+}
+
 static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
     const int W = p.grid_w, H = p.grid_h;
     if (p.radius < 1 || p.radius > 15) return false;
@@ -480,7 +532,16 @@ static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) 
     while (b) { const int tmp = g % b; g = b; b = tmp; }   // gcd(W, 16)
     const int qrows = 16 / g;
     if (qrows * W > 256) return false;
-    const int RPC = (256 / W) / qrows * qrows;
+    // prefer 4 accumulator buffers of 128 TMEM columns (4 independent epilogue groups); else 2 x 256
+    // 4 accumulator buffers of 128 TMEM columns (one epilogue group each) or 2 x 256 (two groups per buffer,
+    // splitting the key rows).  Bigger key tiles amortise the per-tile pipeline overhead better, so 2 x 256 is the
+    // default; TIMET_TC_NBUF=4 selects the other layout for experiments.
+    const char *nb = getenv("TIMET_TC_NBUF");
+    int RPC = (256 / W) / qrows * qrows;
+    G->nbuf = 2;
+    if (nb && atoi(nb) == 4 && (128 / W) / qrows >= 1) { RPC = (128 / W) / qrows * qrows; G->nbuf = 4; }
+    G->buf_cols = 512 / G->nbuf;
+    G->cap = (p.topk <= 5) ? 16 : 32;
     G->H = H; G->W = W; G->N = L.N; G->Dp = L.Dp; G->NKC = L.Dp / 64;
     G->QR = (128 / W) < H ? (128 / W) : H;
     G->tiles_per_frame = (H + G->QR - 1) / G->QR;
@@ -492,18 +553,16 @@ static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) 
     const char *fl = getenv("TIMET_TC_FLAGS");
     G->flags = fl ? atoi(fl) : 0;
     G->total_tiles = (int64_t)p.n_clips * L.nT * G->tiles_per_frame;
-    return true;
+    G->nstages = TC_MAX_STAGES;                                  // as deep a B ring as shared memory allows
+    while (tc_smem_bytes(*G) > 227 * 1024 && G->nstages > 2) G->nstages--;
+    return tc_smem_bytes(*G) <= 227 * 1024;
 }
 
-static size_t tc_smem_bytes(const TcGeom &G) {
-    return 1024 + (size_t)G.NKC * 16384 + (size_t)TC_STAGES * G.NT * 128 + (size_t)2 * TC_CAP * 128 * 4 + sizeof(TcSmemCtl) + 64;
-}
 
 bool ff_tc_supported(const timet_ff_params &p) {
     TcGeom G;
     const FFLayout L = ff_layout(p);
-    if (!tc_geometry(p, L, &G)) return false;
-    return tc_smem_bytes(G) <= 227 * 1024;
+    return tc_geometry(p, L, &G);
 }
 
 int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, const int32_t *qlist,

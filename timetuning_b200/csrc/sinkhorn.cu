@@ -249,6 +249,7 @@ struct SkResArgs {
     float *q_out;
     float *partials;          // [2, grid, K]
     unsigned int *bar;        // monotonic grid-barrier counter (zeroed before launch)
+    unsigned long long *ufix; // [3, K] fixed-point marginal accumulators (zeroed before launch)
     int64_t B;
     int K, iters, rows_per_cta, scores_mode;
     float inv_eps, r, c;
@@ -301,23 +302,23 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
         }
     }
 
+    // ---- R^(0) = column sums of E: per-CTA float partials, grid barrier, fixed-order fold -> a_i = r / R_i
+#pragma unroll
+    for (int v = 0; v < NV4; ++v) {
+        const int i4 = lane + 32 * v;
+        if (i4 < K4) reinterpret_cast<float4 *>(red + warp * K)[i4] = acc[v];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < SKR_WARPS; ++w) t += red[w * K + i];
+        A.partials[(size_t)blockIdx.x * K + i] = t;
+    }
+    grid_barrier(A.bar, (++epoch) * gridDim.x);
+    fold_partials<SKR_THREADS>(A.partials, gridDim.x, K, red, a_s, A.r);
+
     for (int it = 0; it < A.iters; ++it) {
-        // ---- publish this CTA's marginal partial, grid barrier, fold all partials -> a_i = r / R_i
-#pragma unroll
-        for (int v = 0; v < NV4; ++v) {
-            const int i4 = lane + 32 * v;
-            if (i4 < K4) reinterpret_cast<float4 *>(red + warp * K)[i4] = acc[v];
-        }
-        __syncthreads();
-        float *part = A.partials + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * K;
-        for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < SKR_WARPS; ++w) t += red[w * K + i];
-            part[i] = t;
-        }
-        grid_barrier(A.bar, (++epoch) * gridDim.x);
-        fold_partials<SKR_THREADS>(A.partials + (size_t)(it & 1) * gridDim.x * K, gridDim.x, K, red, a_s, A.r);
         float4 av[NV4];
 #pragma unroll
         for (int v = 0; v < NV4; ++v) {
@@ -326,15 +327,15 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
             acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const bool last = (it == A.iters - 1);
-        // ---- sweep the resident rows: s_j = sum_i a_i E_ji ; then either R_i += E_ji * c/s_j or write Q
+        // ---- sweep the resident rows: s_j = sum_i a_i E_ji ; then either u_i += a_i E_ji * c/s_j or write Q
         for (int rl = warp; rl < nrows; rl += SKR_WARPS) {
-            float4 e[NV4], p[NV4];
+            float4 p[NV4];
             float s = 0.f;
 #pragma unroll
             for (int v = 0; v < NV4; ++v) {
                 const int i4 = lane + 32 * v;
-                e[v] = (i4 < K4) ? E[(size_t)rl * K4 + i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                p[v] = make_float4(e[v].x * av[v].x, e[v].y * av[v].y, e[v].z * av[v].z, e[v].w * av[v].w);
+                const float4 e = (i4 < K4) ? E[(size_t)rl * K4 + i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                p[v] = make_float4(e.x * av[v].x, e.y * av[v].y, e.z * av[v].z, e.w * av[v].w);
                 s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
             }
             s = warp_sum(s);
@@ -342,8 +343,8 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
                 const float b = __fdiv_rn(A.c, s);
 #pragma unroll
                 for (int v = 0; v < NV4; ++v) {
-                    acc[v].x = fmaf(e[v].x, b, acc[v].x); acc[v].y = fmaf(e[v].y, b, acc[v].y);
-                    acc[v].z = fmaf(e[v].z, b, acc[v].z); acc[v].w = fmaf(e[v].w, b, acc[v].w);
+                    acc[v].x = fmaf(p[v].x, b, acc[v].x); acc[v].y = fmaf(p[v].y, b, acc[v].y);
+                    acc[v].z = fmaf(p[v].z, b, acc[v].z); acc[v].w = fmaf(p[v].w, b, acc[v].w);
                 }
             } else {
                 const float inv = __fdiv_rn(1.f, s);
@@ -354,6 +355,31 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
                     if (i4 < K4) __stcs(dst + i4, make_float4(p[v].x * inv, p[v].y * inv, p[v].z * inv, p[v].w * inv));
                 }
             }
+        }
+        if (last) break;
+        // ---- marginals of Q itself, u_i = sum_j a_i E_ji b_j (they sum to 1 over i, so 2^-62 fixed point never
+        // overflows): integer atomics are associative -> the grid-wide sum is bit-reproducible without a fold.
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            if (i4 < K4) reinterpret_cast<float4 *>(red + warp * K)[i4] = acc[v];
+        }
+        __syncthreads();
+        unsigned long long *ufix = A.ufix + (size_t)(it % 3) * K;
+        for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < SKR_WARPS; ++w) t += red[w * K + i];
+            atomicAdd(ufix + i, (unsigned long long)__float2ll_rn(t * 4611686018427387904.0f));
+        }
+        grid_barrier(A.bar, (++epoch) * gridDim.x);
+        for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
+            const float u = (float)((double)(long long)__ldcg(ufix + i) * 2.168404344971009e-19);   // * 2^-62
+            a_s[i] = a_s[i] * __fdiv_rn(A.r, u);                       // Q *= r / u  (my_utils.py:268)
+        }
+        if (blockIdx.x == 0) {                                         // recycle the buffer of iteration it-1 for it+2
+            unsigned long long *z = A.ufix + (size_t)((it + 2) % 3) * K;
+            for (int i = threadIdx.x; i < K; i += SKR_THREADS) z[i] = 0ull;
         }
         __syncthreads();
     }
@@ -425,7 +451,7 @@ size_t timet_sinkhorn_workspace_bytes(int64_t B, int K) {
     (void)B;
     if (K < 1) return 0;
     const size_t grid_max = 2 * 160;   // >= 2 * SM count on every B200 SKU
-    return align_up((grid_max + 2) * (size_t)K * sizeof(float) + 256, 256);
+    return align_up((grid_max + 2) * (size_t)K * sizeof(float) + 256 + 3 * (size_t)K * sizeof(unsigned long long) + 64, 256);
 }
 
 int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
@@ -450,8 +476,12 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
             (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160) {
             float *partials = (float *)workspace;
             unsigned int *bar = (unsigned int *)(partials + (size_t)322 * K);
-            TIMET_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned int), st));
+            // bar (64 B slot) followed by the 8-byte aligned fixed-point buffers; one memset clears both
+            const size_t bar_off = (size_t)322 * K * sizeof(float);
+            const size_t ufix_off = align_up(bar_off + 64, 64);
+            TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 3 * (size_t)K * sizeof(unsigned long long), st));
             SkResArgs R;
+            R.ufix = (unsigned long long *)((char *)workspace + ufix_off);
             R.in = in; R.q_out = q_out; R.partials = partials; R.bar = bar; R.B = B; R.K = K; R.iters = iters;
             R.rows_per_cta = rpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
             R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
