@@ -138,6 +138,11 @@ int timet_ff_export_selection(const timet_ff_params *p, const void *workspace, s
 int timet_debug_tc_tile(const timet_ff_params *p, void *workspace, size_t workspace_bytes, int64_t tile_id,
                         float *dump, timet_stream_t stream);
 
+/* Test hook: with env TIMET_TC_TRACE=1 the tensor-core kernel stamps %globaltimer at 8 points of every CTA's
+ * life; this copies [n_ctas, 8] uint64 ns (device -> device) for timeline analysis (profiles/tc_trace.py). */
+int timet_debug_tc_trace(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, uint64_t *out,
+                         int n_ctas, timet_stream_t stream);
+
 /* ------------------------------------------------------------------ small routines
  * restrict_neighborhood(h, w, s)  mask_propagation.py:377-391 -> float32 [h*w, h*w] of 0/1
  * norm_mask(mask)                 mask_propagation.py:363-374 -> per-channel min-max, [C, HW];

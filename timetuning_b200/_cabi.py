@@ -39,6 +39,7 @@ _PROTOS = {
     "timet_ff_slots": (C.c_int, [C.POINTER(FFParams)]),
     "timet_ff_export_selection": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, C.c_int, C.c_int, _P, _P, _P, _P]),
     "timet_debug_tc_tile": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, C.c_int64, _P, _P]),
+    "timet_debug_tc_trace": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, _P, C.c_int, _P]),
     "timet_restrict_neighborhood": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
     "timet_norm_mask": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P]),
     "timet_comm_unique_id": (C.c_int, [_P]),

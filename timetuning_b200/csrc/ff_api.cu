@@ -137,4 +137,14 @@ int timet_debug_tc_tile(const timet_ff_params *p, void *workspace, size_t worksp
     return ff_tc_debug_tile(*p, L, (char *)workspace, tile_id, dump, (cudaStream_t)stream);
 }
 
+
+int timet_debug_tc_trace(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, uint64_t *out, int n_ctas,
+                         timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(out != nullptr, "debug_tc_trace: out is NULL");
+    return ff_tc_debug_trace(*p, L, (const char *)workspace, (unsigned long long *)out, n_ctas, (cudaStream_t)stream);
+}
+
 }

@@ -47,8 +47,8 @@ struct TcGeom {
     int RPC, NT, qrows;
     int n_clips, n_frames, nT, t_begin, n_last, radius, topk;
     int nbuf, buf_cols, nstages;   // TMEM accumulator buffers (4 x 128 or 2 x 256 columns), B ring depth
-    int cap;                       // candidate slots per (query, group): 16 (topk <= 5) or 32
     int trig;                 // compaction trigger
+    int clip_group;           // clips whose tiles are launched together (L2 locality); env TIMET_TC_CLIP_GROUP
     int flags;                // debug (env TIMET_TC_FLAGS): 1 = epilogue releases tiles unscanned, 2 = scan but never append
     int64_t total_tiles;
 };
@@ -65,6 +65,7 @@ __device__ __forceinline__ float thr_dec(uint32_t v) { return __uint_as_float(v)
 
 __device__ __forceinline__ float tc_decode(uint32_t entry) { return (float)(entry >> 13) * (1.0f / 131072.0f) - 2.0f; }
 
+// Candidate lists live in shared memory: slot s of thread qi of group g at list + s * 512 B (conflict-free).
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -94,6 +95,23 @@ __device__ __forceinline__ void tc_offer(uint32_t &slot_addr, float v, float thr
         : "memory");
 }
 
+// Drop entries below thr.  Warp-synchronous (loop bound = warp max of cnt).
+__device__ __forceinline__ void tc_filter(uint32_t list, int &cnt, float thr) {
+    int maxcnt = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
+    // keep entries whose quantised value is >= thr (quantisation is already inside FF_TC_SLACK)
+    const float lim = (thr + 2.0f) * 131072.0f;
+    const uint32_t enc = (lim <= 0.f) ? 0u : ((uint32_t)lim << 13);
+    uint32_t dst = list;
+#pragma unroll 4
+    for (int s = 0; s < maxcnt; ++s) {
+        const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
+        if (s < cnt && e >= enc) { sts_u32(dst, e); dst += TC_SLOT_STRIDE; }
+    }
+    cnt = (int)((dst - list) / TC_SLOT_STRIDE);
+}
+
 // Raise thr from the list content and drop entries that can no longer be among the top-k.
 // One pass over the list keeps the 8 largest packed entries in sorted registers (max/min chain), so the
 // k-th largest (k <= 8) is read off directly.  Warp-synchronous; loop bounds are warp-uniform.
@@ -119,40 +137,15 @@ __device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, 
 #pragma unroll
     for (int j = 1; j < 8; ++j) kth = (k - 1 == j) ? top[j] : kth;
     if (kth != 0u) thr = fmaxf(thr, tc_decode(kth) - FF_TC_SLACK);
-    // keep entries whose quantised value is >= thr (quantisation is already inside FF_TC_SLACK)
-    const float lim = (thr + 2.0f) * 131072.0f;
-    const uint32_t enc = (lim <= 0.f) ? 0u : ((uint32_t)lim << 13);
-    uint32_t dst = list;
-#pragma unroll 4
-    for (int s = 0; s < maxcnt; ++s) {
-        const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
-        if (s < cnt && e >= enc) { sts_u32(dst, e); dst += TC_SLOT_STRIDE; }
-    }
-    int j = (int)((dst - list) / TC_SLOT_STRIDE);
-    if (j > keep_max) { j = keep_max; lost = 1; }
-    cnt = j;
-}
-
-// Drop entries below thr (no k-th search).  Warp-synchronous.
-__device__ __forceinline__ void tc_filter(uint32_t list, int &cnt, float thr) {
-    int maxcnt = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
-    const float lim = (thr + 2.0f) * 131072.0f;
-    const uint32_t enc = (lim <= 0.f) ? 0u : ((uint32_t)lim << 13);
-    uint32_t dst = list;
-    for (int s = 0; s < maxcnt; ++s) {
-        const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
-        if (s < cnt && e >= enc) { sts_u32(dst, e); dst += TC_SLOT_STRIDE; }
-    }
-    cnt = (int)((dst - list) / TC_SLOT_STRIDE);
+    tc_filter(list, cnt, thr);
+    if (cnt > keep_max) { cnt = keep_max; lost = 1; }
 }
 
 template <bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom G,
-             uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, int64_t tile_override,
-             float *__restrict__ dump) {
+             uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, uint32_t *__restrict__ scratch,
+             int64_t tile_override, float *__restrict__ dump, unsigned long long *__restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
     // carve: [A: NKC x 16 KB][B: nstages x NT*128][lists: 4 x 32 x 128 u32][ctl]; 1024-aligned for SWIZZLE_128B
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -160,23 +153,32 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const uint32_t b_stage_bytes = (uint32_t)G.NT * 128u;
     uint8_t *sB = sA + (size_t)G.NKC * 16384;
     uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * b_stage_bytes);
-    TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(sList + TC_GROUPS * G.cap * 128);
+    TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(sList + TC_GROUPS * TC_CAP * 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // debug timeline: stamp s of this CTA (globaltimer ns); trace == nullptr in production
+    auto stamp = [&](int s) {
+        if (trace && blockIdx.x < FF_TRACE_CTAS) {
+            unsigned long long tns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+            trace[(size_t)blockIdx.x * FF_TRACE_SLOTS + s] = tns;
+        }
+    };
+    if (threadIdx.x == 0) stamp(0);
 
     // ---- which tile: heavy (late) target frames first
     const int64_t tile_id = (tile_override >= 0) ? tile_override : (int64_t)blockIdx.x;
     // launch order: groups of TC_CLIP_GROUP clips (their frames stay L2-resident while the group runs),
     // inside a group the heavy (late) target frames first
     const int per_clip = G.nT * G.tiles_per_frame;
-    const int grp = (int)(tile_id / ((int64_t)TC_CLIP_GROUP * per_clip));
-    const int grp_clips = min(TC_CLIP_GROUP, G.n_clips - grp * TC_CLIP_GROUP);
-    const int in_grp = (int)(tile_id - (int64_t)grp * TC_CLIP_GROUP * per_clip);
+    const int grp = (int)(tile_id / ((int64_t)G.clip_group * per_clip));
+    const int grp_clips = min(G.clip_group, G.n_clips - grp * G.clip_group);
+    const int in_grp = (int)(tile_id - (int64_t)grp * G.clip_group * per_clip);
     const int per_t = grp_clips * G.tiles_per_frame;
     const int tdesc = in_grp / per_t;
     const int rem = in_grp - tdesc * per_t;
     const int t = G.n_frames - 1 - tdesc;
-    const int clip = grp * TC_CLIP_GROUP + rem / G.tiles_per_frame, qt = rem % G.tiles_per_frame;
+    const int clip = grp * G.clip_group + rem / G.tiles_per_frame, qt = rem % G.tiles_per_frame;
     const int qr0 = qt * G.QR;
     const int qr1 = min(G.H - 1, qr0 + G.QR - 1);
     const int nq = (qr1 - qr0 + 1) * G.W;
@@ -205,6 +207,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
+    if (threadIdx.x == 0) stamp(1);
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -231,6 +234,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (lane == 0) {
             ptx::mbar_wait(&ctl->a_full, 0);
             ptx::tc_fence_after();
+            stamp(2);
             const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
             int it = 0;
             for (int tile = 0; tile < ntiles; ++tile) {
@@ -259,6 +263,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 }
                 ptx::umma_commit(&ctl->tmem_full[buf]);            // accumulator ready for its epilogue group
             }
+            stamp(3);
         }
     } else if (warp >= 4) {
         // =========================== epilogue groups ===========================
@@ -269,8 +274,8 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const int row_par = (G.nbuf == 4) ? -1 : (g >> 1);
         const int qi = ((warp & 3) << 5) + lane;                    // TMEM lane == query row of the tile
         const uint32_t lane_base = (uint32_t)((warp & 3) << 5) << 16;
-        const uint32_t list = ptx::smem_u32(sList + (size_t)g * G.cap * 128 + qi);   // slot s at list + s * 512 B
-        const int half = G.cap >> 1;                                  // max entries kept across a compaction
+        const uint32_t list = ptx::smem_u32(sList + (size_t)g * TC_CAP * 128 + qi);   // slot s at list + s * 512 B
+        constexpr int half = TC_CAP / 2;                              // max entries kept across a compaction
         const bool valid = qi < nq;
         const int qrow = qr0 + qi / G.W, qcol = qi % G.W;
         const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
@@ -284,7 +289,8 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             const int kr_start = kr_lo + ch * G.RPC;
             const int rc = min(G.RPC, kr_hi + 1 - kr_start);
             const uint32_t use = (uint32_t)(tile / G.nbuf);
-            ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u);
+            if (lane == 0) ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u);   // one poller per warp: the tensor core needs the smem bandwidth
+            __syncwarp();
             ptx::tc_fence_after();
             const uint32_t t_acc = tmem_base + (uint32_t)(buf * G.buf_cols) + lane_base;
             thr = fmaxf(thr, thr_dec(ctl->thr_sh[qi]));               // what the other groups have established
@@ -322,15 +328,6 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 #define TC_OFFER(E) tc_offer<(1u << (E))>(slot, __uint_as_float(r[E]), thr, wmask, code0 + (E));
                     // invariant: cnt <= cap/2 before every run of cap/2 offers -> the cap slots cannot overflow
                     TC_OFFER(0) TC_OFFER(1) TC_OFFER(2) TC_OFFER(3) TC_OFFER(4) TC_OFFER(5) TC_OFFER(6) TC_OFFER(7)
-                    if (G.cap == 16) {
-                        cnt = (int)((slot - list) / TC_SLOT_STRIDE);
-                        if (__any_sync(0xffffffffu, cnt > half)) {
-                            const float before = thr;
-                            tc_compact(list, cnt, thr, lost, G.topk, half);
-                            if (thr > before) atomicMax(&ctl->thr_sh[qi], thr_enc(thr));
-                            slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
-                        }
-                    }
                     TC_OFFER(8) TC_OFFER(9) TC_OFFER(10) TC_OFFER(11) TC_OFFER(12) TC_OFFER(13) TC_OFFER(14) TC_OFFER(15)
 #undef TC_OFFER
                     cnt = (int)((slot - list) / TC_SLOT_STRIDE);
@@ -347,6 +344,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
         }
 
+        if (warp == 4 && lane == 0) stamp(4);
         // ---- final: agree on the per-query threshold, filter, merge the 4 lists, publish <= FF_CAND_STORE candidates
         if (!DUMP) {
             {
@@ -359,18 +357,19 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             tc_filter(list, cnt, thr);
             if (g > 0) ctl->xchg[g - 1][qi] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (warp == 4 && lane == 0) stamp(5);
             if (g == 0) {
                 for (int og = 1; og < TC_GROUPS; ++og) {
                     const uint32_t other = ctl->xchg[og - 1][qi];
                     const int ocnt = (int)(other & 0xFFFFu);
                     lost |= (int)(other >> 16);
-                    const uint32_t olist = list + (uint32_t)og * (uint32_t)G.cap * 128u * 4u;
+                    const uint32_t olist = list + (uint32_t)og * TC_CAP * 128u * 4u;
                     for (int s = 0; s < ocnt; ++s) {
-                        if (cnt < G.cap) { sts_u32(list + (uint32_t)cnt * TC_SLOT_STRIDE, lds_u32(olist + s * TC_SLOT_STRIDE)); ++cnt; }
+                        if (cnt < TC_CAP) { sts_u32(list + (uint32_t)cnt * TC_SLOT_STRIDE, lds_u32(olist + s * TC_SLOT_STRIDE)); ++cnt; }
                         else lost = 1;
                     }
                 }
-                tc_compact(list, cnt, thr, lost, G.topk, min(G.cap, FF_CAND_STORE));   // joint k-th - slack
+                tc_compact(list, cnt, thr, lost, G.topk, FF_CAND_STORE);   // joint k-th - slack
                 if (valid && tile_override < 0) {
                     const int64_t q = ((int64_t)clip * G.nT + (t - G.t_begin)) * G.N + qr0 * G.W + qi;
                     uint32_t *dst = cand + q * FF_CAND_STORE;
@@ -390,8 +389,10 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
 
     // ---- teardown
+    if (warp == 4 && lane == 0) stamp(6);
     ptx::tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(7);
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
@@ -520,7 +521,7 @@ static int make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int 
 }
 
 static size_t tc_smem_bytes(const TcGeom &G) {
-    return 1024 + (size_t)G.NKC * 16384 + (size_t)G.nstages * G.NT * 128 + (size_t)TC_GROUPS * G.cap * 128 * 4 + sizeof(TcSmemCtl) + 64;
+    return 1024 + (size_t)G.NKC * 16384 + (size_t)G.nstages * G.NT * 128 + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(TcSmemCtl) + 64;
 }
 
 static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
@@ -541,7 +542,6 @@ static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) 
     G->nbuf = 2;
     if (nb && atoi(nb) == 4 && (128 / W) / qrows >= 1) { RPC = (128 / W) / qrows * qrows; G->nbuf = 4; }
     G->buf_cols = 512 / G->nbuf;
-    G->cap = (p.topk <= 5) ? 16 : 32;
     G->H = H; G->W = W; G->N = L.N; G->Dp = L.Dp; G->NKC = L.Dp / 64;
     G->QR = (128 / W) < H ? (128 / W) : H;
     G->tiles_per_frame = (H + G->QR - 1) / G->QR;
@@ -552,8 +552,12 @@ static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) 
     G->trig = 16; (void)side;
     const char *fl = getenv("TIMET_TC_FLAGS");
     G->flags = fl ? atoi(fl) : 0;
+    const char *cg = getenv("TIMET_TC_CLIP_GROUP");
+    G->clip_group = (cg && atoi(cg) >= 1) ? atoi(cg) : TC_CLIP_GROUP;
     G->total_tiles = (int64_t)p.n_clips * L.nT * G->tiles_per_frame;
     G->nstages = TC_MAX_STAGES;                                  // as deep a B ring as shared memory allows
+    const char *ns = getenv("TIMET_TC_STAGES");
+    if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G->nstages = atoi(ns);
     while (tc_smem_bytes(*G) > 227 * 1024 && G->nstages > 2) G->nstages--;
     return tc_smem_bytes(*G) <= 227 * 1024;
 }
@@ -583,7 +587,10 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
     TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t *cand = reinterpret_cast<uint32_t *>(ws + L.off_cand);
     uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_cand_meta);
-    ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, -1, nullptr);
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + L.off_scratch);
+    const char *tr = getenv("TIMET_TC_TRACE");
+    unsigned long long *trace = (tr && tr[0] == '1') ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
+    ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, scratch, -1, nullptr, trace);
     TIMET_LAUNCHED();
 
     unsigned int *redo_count = reinterpret_cast<unsigned int *>(ws + L.off_redo);
@@ -618,8 +625,15 @@ int ff_tc_debug_tile(const timet_ff_params &p, const FFLayout &L, char *ws, int6
     if ((rc = make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
     const size_t smem = tc_smem_bytes(G);
     TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ff_tc_kernel<true><<<1, TC_THREADS, smem, st>>>(map_a, map_b, G, nullptr, nullptr, tile_id, dump);
+    ff_tc_kernel<true><<<1, TC_THREADS, smem, st>>>(map_a, map_b, G, nullptr, nullptr, reinterpret_cast<uint32_t *>(ws + L.off_scratch), tile_id, dump, nullptr);
     TIMET_LAUNCHED();
+    return TIMET_OK;
+}
+
+int ff_tc_debug_trace(const timet_ff_params &p, const FFLayout &L, const char *ws, unsigned long long *out, int n_ctas, cudaStream_t st) {
+    (void)p;
+    TIMET_CHECK_ARG(n_ctas >= 1 && n_ctas <= FF_TRACE_CTAS, "debug trace: n_ctas out of range");
+    TIMET_CUDA(cudaMemcpyAsync(out, ws + L.off_trace, (size_t)n_ctas * FF_TRACE_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     return TIMET_OK;
 }
 
