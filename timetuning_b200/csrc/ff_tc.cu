@@ -26,120 +26,10 @@
 //               shared memory; warp-synchronous compaction raises the threshold.
 #include <stdlib.h>
 
-#include "ff_select.cuh"
-#include "ptx_sm100.cuh"
+#include "ff_tc_dev.cuh"
 
 namespace timet {
 
-constexpr int TC_GROUPS = 4;                    // epilogue warpgroups (4 warps each)
-constexpr int TC_THREADS = 128 + TC_GROUPS * 128;
-constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_MAX_NKC = 6;                  // resident query tile: Dp <= 384
-constexpr int TC_CLIP_GROUP = 8;                // clips whose tiles are launched together (L2 locality)
-constexpr int TC_CAP = FF_CAND_CAP;            // 32 candidates per (query, epilogue group)
-constexpr float FF_TC_DELTA = 1.05e-3f;        // bound on |sim~ - sim|: fp16 RN of both unit vectors (2^-10) + fp32 accumulation
-constexpr float FF_TC_SLACK = 2.0f * FF_TC_DELTA + 3.1e-5f;   // + 2 x fixed-point quantisation (2^-17) with margin
-constexpr float TC_FIX_BIAS = 66.0f;           // sim~ + 2 in [1,3] lands in [64,128): ulp = 2^-17 -> 19-bit fixed point in the mantissa
-
-struct TcGeom {
-    int H, W, N, Dp, NKC;
-    int QR, tiles_per_frame;
-    int RPC, NT, qrows;
-    int n_clips, n_frames, nT, t_begin, n_last, radius, topk;
-    int nbuf, buf_cols, nstages;   // TMEM accumulator buffers (4 x 128 or 2 x 256 columns), B ring depth
-    int trig;                 // compaction trigger
-    int clip_group;           // clips whose tiles are launched together (L2 locality); env TIMET_TC_CLIP_GROUP
-    int flags;                // debug (env TIMET_TC_FLAGS): 1 = epilogue releases tiles unscanned, 2 = scan but never append
-    int64_t total_tiles;
-};
-
-struct __align__(8) TcSmemCtl {
-    uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], a_full, tmem_full[4], tmem_empty[4];
-    uint32_t tmem_base;
-    uint32_t thr_sh[128];     // per-query nomination threshold shared by the groups: float bits of (thr + 4), atomicMax
-    uint32_t xchg[3][128];    // groups 1..3 -> group 0: cnt | lost << 16 per query
-};
-
-__device__ __forceinline__ uint32_t thr_enc(float thr) { return __float_as_uint(fmaxf(thr, -3.0f) + 4.0f); }
-__device__ __forceinline__ float thr_dec(uint32_t v) { return __uint_as_float(v) - 4.0f; }
-
-__device__ __forceinline__ float tc_decode(uint32_t entry) { return (float)(entry >> 13) * (1.0f / 131072.0f) - 2.0f; }
-
-// Candidate lists live in shared memory: slot s of thread qi of group g at list + s * 512 B (conflict-free).
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-constexpr uint32_t TC_SLOT_STRIDE = 128u * 4u;     // bytes between consecutive slots of one thread's list
-
-// One epilogue step, predicated (no branch): if the key is inside the window (bit BIT of wmask) and
-// sim~ > thr, append the packed candidate ((sim~ + 2) in 19-bit fixed point << 13 | code) and advance.
-template <uint32_t BIT>
-__device__ __forceinline__ void tc_offer(uint32_t &slot_addr, float v, float thr, uint32_t wmask, uint32_t code) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b32 u;\n\t.reg .f32 t;\n\t"
-        "and.b32 u, %3, %5;\n\t"
-        "setp.ne.b32 p, u, 0;\n\t"
-        "setp.gt.and.f32 p, %1, %2, p;\n\t"
-        "@p add.rn.f32 t, %1, 0f42840000;\n\t"     // + 66.0f
-        "@p mov.b32 u, t;\n\t"
-        "@p mad.lo.u32 u, u, 8192, %4;\n\t"
-        "@p st.shared.u32 [%0], u;\n\t"
-        "@p add.u32 %0, %0, 512;\n\t}"
-        : "+r"(slot_addr)
-        : "f"(v), "f"(thr), "r"(wmask), "r"(code), "n"(BIT)
-        : "memory");
-}
-
-// Drop entries below thr.  Warp-synchronous (loop bound = warp max of cnt).
-__device__ __forceinline__ void tc_filter(uint32_t list, int &cnt, float thr) {
-    int maxcnt = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
-    // keep entries whose quantised value is >= thr (quantisation is already inside FF_TC_SLACK)
-    const float lim = (thr + 2.0f) * 131072.0f;
-    const uint32_t enc = (lim <= 0.f) ? 0u : ((uint32_t)lim << 13);
-    uint32_t dst = list;
-#pragma unroll 4
-    for (int s = 0; s < maxcnt; ++s) {
-        const uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
-        if (s < cnt && e >= enc) { sts_u32(dst, e); dst += TC_SLOT_STRIDE; }
-    }
-    cnt = (int)((dst - list) / TC_SLOT_STRIDE);
-}
-
-// Raise thr from the list content and drop entries that can no longer be among the top-k.
-// One pass over the list keeps the 8 largest packed entries in sorted registers (max/min chain), so the
-// k-th largest (k <= 8) is read off directly.  Warp-synchronous; loop bounds are warp-uniform.
-// Afterwards cnt <= keep_max (entries beyond that are dropped and the query is flagged for the exact re-do).
-__device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, int &lost, int k, int keep_max) {
-    int maxcnt = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
-    uint32_t top[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) top[j] = 0u;
-#pragma unroll 4
-    for (int s = 0; s < maxcnt; ++s) {
-        uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t hi = max(e, top[j]);
-            e = min(e, top[j]);
-            top[j] = hi;
-        }
-    }
-    uint32_t kth = top[0];
-#pragma unroll
-    for (int j = 1; j < 8; ++j) kth = (k - 1 == j) ? top[j] : kth;
-    if (kth != 0u) thr = fmaxf(thr, tc_decode(kth) - FF_TC_SLACK);
-    tc_filter(list, cnt, thr);
-    if (cnt > keep_max) { cnt = keep_max; lost = 1; }
-}
 
 template <bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -214,17 +104,16 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (lane == 0) {
             ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
             for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, q_row0, &ctl->a_full);
-            int it = 0;
+            uint32_t stage = 0, phase = 0;                     // ring position without divisions
             for (int ci = 0; ci < nctx; ++ci) {
                 const int f = ctx_frame(t, G.n_last, ci);
                 for (int ch = 0; ch < nchunks; ++ch) {
                     const int k_row0 = (int)(clip_row0 + (int64_t)f * G.N + (kr_lo + ch * G.RPC) * G.W);
-                    for (int kc = 0; kc < G.NKC; ++kc, ++it) {
-                        const int stage = it % G.nstages;
-                        const uint32_t ph = (uint32_t)(it / G.nstages) & 1u;
-                        ptx::mbar_wait(&ctl->empty[stage], ph ^ 1u);
+                    for (int kc = 0; kc < G.NKC; ++kc) {
+                        ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
                         ptx::mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
                         ptx::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, kc * 64, k_row0, &ctl->full[stage]);
+                        if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
@@ -235,33 +124,34 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             ptx::mbar_wait(&ctl->a_full, 0);
             ptx::tc_fence_after();
             stamp(2);
-            const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
-            int it = 0;
+            // the issuing thread is on the critical path of every MMA: descriptors are built once and advanced by
+            // adding to the 14-bit start-address field; the ring position is tracked without divisions
+            const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sA)), db0 = ptx::umma_desc_sw128(ptx::smem_u32(sB));
+            const uint32_t stage_step = b_stage_bytes >> 4;
+            uint32_t stage = 0, phase = 0, buf = 0, use = 0;
+            int ch = 0;
             for (int tile = 0; tile < ntiles; ++tile) {
-                const int ch = tile % nchunks;
-                const int rows_left = kr_hi + 1 - (kr_lo + ch * G.RPC);
-                const int rc = min(G.RPC, rows_left);
+                const int rc = min(G.RPC, kr_hi + 1 - (kr_lo + ch * G.RPC));
                 const int n_mma = min(G.NT, (rc + G.qrows - 1) / G.qrows * G.qrows * G.W);
                 const uint32_t idesc = ptx::umma_idesc_f16(128, n_mma);
-                const int buf = tile % G.nbuf;
-                const uint32_t use = (uint32_t)(tile / G.nbuf);
                 ptx::mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * G.buf_cols);
-                for (int kc = 0; kc < G.NKC; ++kc, ++it) {
-                    const int stage = it % G.nstages;
-                    const uint32_t ph = (uint32_t)(it / G.nstages) & 1u;
-                    ptx::mbar_wait(&ctl->full[stage], ph);
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)G.buf_cols;
+                uint64_t da = da0;
+                for (int kc = 0; kc < G.NKC; ++kc, da += 16384 >> 4) {
+                    ptx::mbar_wait(&ctl->full[stage], phase);
                     ptx::tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = ptx::umma_desc_sw128(a_addr + kc * 16384 + k * 32);
-                        const uint64_t db = ptx::umma_desc_sw128(b_addr + stage * b_stage_bytes + k * 32);
-                        ptx::umma_f16(d_tmem, da, db, idesc, (kc | k) != 0);
-                    }
+                    const uint64_t db = db0 + (uint64_t)(stage * stage_step);
+                    ptx::umma_f16(d_tmem, da, db, idesc, kc != 0);
+                    ptx::umma_f16(d_tmem, da + 2, db + 2, idesc, true);      // +32 B per K = 16 step
+                    ptx::umma_f16(d_tmem, da + 4, db + 4, idesc, true);
+                    ptx::umma_f16(d_tmem, da + 6, db + 6, idesc, true);
                     ptx::umma_commit(&ctl->empty[stage]);          // frees the smem stage when the MMAs retire
+                    if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit(&ctl->tmem_full[buf]);            // accumulator ready for its epilogue group
+                if (++buf == (uint32_t)G.nbuf) { buf = 0; ++use; }
+                if (++ch == nchunks) ch = 0;
             }
             stamp(3);
         }
@@ -500,7 +390,7 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-static int make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int box_rows) {
+int tc_make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int box_rows) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -520,11 +410,11 @@ static int make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int 
     return TIMET_OK;
 }
 
-static size_t tc_smem_bytes(const TcGeom &G) {
+size_t tc_smem_bytes(const TcGeom &G) {
     return 1024 + (size_t)G.NKC * 16384 + (size_t)G.nstages * G.NT * 128 + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(TcSmemCtl) + 64;
 }
 
-static bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
+bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
     const int W = p.grid_w, H = p.grid_h;
     if (p.radius < 1 || p.radius > 15) return false;
     if (p.n_last_frames > 7 || p.topk > 8) return false;   // 3-bit context slot in the packed candidate; k + ties must fit 16 slots
@@ -572,26 +462,34 @@ bool ff_tc_supported(const timet_ff_params &p) {
 int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, const int32_t *qlist,
                         const unsigned int *qcount, int64_t max_items, cudaStream_t st);
 
+int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
+
 int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
     TcGeom G;
     if (!tc_geometry(p, L, &G)) {
         set_error("tensor-core engine: unsupported shape");
         return TIMET_ERR_UNSUPPORTED;
     }
-    const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
-    CUtensorMap map_a, map_b;
     int rc;
-    if ((rc = make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
-    if ((rc = make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
-    const size_t smem = tc_smem_bytes(G);
-    TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t *cand = reinterpret_cast<uint32_t *>(ws + L.off_cand);
     uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_cand_meta);
-    uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + L.off_scratch);
-    const char *tr = getenv("TIMET_TC_TRACE");
-    unsigned long long *trace = (tr && tr[0] == '1') ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
-    ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, scratch, -1, nullptr, trace);
-    TIMET_LAUNCHED();
+    // nomination: 1-CTA kernel by default; TIMET_TC_PAIR=1 selects the CTA-pair kernel (cta_group::2, ff_tc2.cu)
+    const char *pe = getenv("TIMET_TC_PAIR");
+    rc = (pe && pe[0] == '1') ? ff_select_tc_pair_launch(p, L, ws, st) : TIMET_ERR_UNSUPPORTED;   // opt-in
+    if (rc != TIMET_OK && rc != TIMET_ERR_UNSUPPORTED) return rc;
+    if (rc == TIMET_ERR_UNSUPPORTED) {
+        const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
+        CUtensorMap map_a, map_b;
+        if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+        if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
+        const size_t smem = tc_smem_bytes(G);
+        TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + L.off_scratch);
+        const char *tr = getenv("TIMET_TC_TRACE");
+        unsigned long long *trace = (tr && tr[0] == '1') ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
+        ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, scratch, -1, nullptr, trace);
+        TIMET_LAUNCHED();
+    }
 
     unsigned int *redo_count = reinterpret_cast<unsigned int *>(ws + L.off_redo);
     int32_t *redo_list = reinterpret_cast<int32_t *>(ws + L.off_redo + 256);
@@ -621,8 +519,8 @@ int ff_tc_debug_tile(const timet_ff_params &p, const FFLayout &L, char *ws, int6
     const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
     CUtensorMap map_a, map_b;
     int rc;
-    if ((rc = make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
-    if ((rc = make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
+    if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+    if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
     const size_t smem = tc_smem_bytes(G);
     TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ff_tc_kernel<true><<<1, TC_THREADS, smem, st>>>(map_a, map_b, G, nullptr, nullptr, reinterpret_cast<uint32_t *>(ws + L.off_scratch), tile_id, dump, nullptr);
