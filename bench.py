@@ -204,9 +204,10 @@ def main():
 
     def step(x_hs, x_ht, x_bb, record=False):
         """staged form of timetuning_b200.step.ff_sinkhorn_step so the selection kernel can be timed live"""
-        s_src = F.normalize(x_hs.reshape(bs * N, -1), dim=-1, p=2) @ d_pr.t()
-        s_tgt = F.normalize(x_ht.reshape(bs * N, -1), dim=-1, p=2) @ d_pr.t()
-        e = [ev() for _ in range(6)] if record else None
+        e = [ev() for _ in range(7)] if record else None
+        if record: e[6].record()
+        s_src = ops.cosine_scores(x_hs.reshape(bs * N, -1), d_pr)
+        s_tgt = ops.cosine_scores(x_ht.reshape(bs * N, -1), d_pr)
         if record: e[0].record()
         q_src = ops.sinkhorn_from_scores(s_src, CFG["epsilon"], CFG["iters"], world)
         q_tgt = ops.sinkhorn_from_scores(s_tgt, CFG["epsilon"], CFG["iters"], world)
@@ -276,6 +277,7 @@ def main():
     # ---- per-stage device times (CUDA events recorded inside the timed region, same stream)
     names = ["sinkhorn_x2", "label_init", "prepare", "select", "gather"]
     stage_ms = {n: sum(e[i].elapsed_time(e[i + 1]) for e in stage_ev) / len(stage_ev) for i, n in enumerate(names)}
+    stage_ms["cosine_scores_x2"] = sum(e[6].elapsed_time(e[0]) for e in stage_ev) / len(stage_ev)
     st = plan.stats()
 
     if rank == 0:

@@ -66,6 +66,15 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
                    int world_size, timet_comm_t comm, float *q_out, void *workspace,
                    size_t workspace_bytes, timet_stream_t stream);
 
+/* ------------------------------------------------------------------ cosine scores
+ * No-grad branch of TimeT.get_feature_prototype_similarity (time_tuning.py:130-141):
+ *   scores[B, K] = F.normalize(x[B, dh], dim=-1) @ prototypes[K, dh]^T      (float32 in / out)
+ * computed on the tensor cores with an fp16 hi/lo split (3 products, <= 2^-22 relative error), because the
+ * scores feed exp(s / eps).  The student branch that needs autograd stays in PyTorch. */
+size_t timet_cosine_scores_workspace_bytes(int64_t B, int K, int dh);
+int timet_cosine_scores(const float *x, const float *prototypes, int64_t B, int K, int dh, float *scores_out,
+                        void *workspace, size_t workspace_bytes, timet_stream_t stream);
+
 /* ------------------------------------------------------------------ Feature-Forwarding
  * Stands behind  label_propagation(...)  mask_propagation.py:396-445   (one target frame)
  *                propagate_labels(...)   mask_propagation.py:448-496   (frame loop + FIFO)

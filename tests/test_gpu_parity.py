@@ -292,3 +292,18 @@ def test_host_pipeline_matches_device_step():
     torch.cuda.synchronize()
     assert torch.equal(q1, q2) and torch.equal(t1, t2)
     assert torch.equal(h1.cpu(), h2)
+
+
+@pytest.mark.parametrize("B,K,dh", [(25088, 200, 256), (392, 200, 256), (1000, 300, 256), (77, 21, 96), (300, 520, 64)])
+def test_cosine_scores(B, K, dh):
+    """timet_cosine_scores (fp16 hi/lo split on tensor cores) vs F.normalize(x) @ prototypes.t() in float64."""
+    rng = np.random.default_rng(B + K)
+    x = (rng.standard_normal((B, dh)) * rng.uniform(0.1, 5.0, size=(B, 1))).astype(np.float32)
+    p = synth.prototypes(K, dh, seed=K)
+    got = tb.cosine_scores(cu(x), cu(p)).cpu().numpy()
+    xn = x.astype(np.float64) / np.maximum(np.linalg.norm(x.astype(np.float64), axis=1, keepdims=True), 1e-12)
+    want = xn @ p.astype(np.float64).T
+    err = np.abs(got - want).max()
+    assert err < 2e-6, f"max abs err {err:.3e}"
+    ref32 = (torch.nn.functional.normalize(cu(x), dim=-1) @ cu(p).t()).cpu().numpy()
+    assert np.abs(got - ref32).max() < 2e-6

@@ -4,10 +4,10 @@ Only the one data-parallel hot path named by BASELINE.json's north_star lives he
 sm_100a CUDA (csrc/) behind a C ABI (include/timet_b200.h) and the Python mirror of the reference's
 callables (ops.py).  `install()` binds them over the reference's module attributes.
 """
-from .ops import (FFPlan, FF_AUTO, FF_EXACT, FF_TC, label_propagation, norm_mask, propagate_labels,  # noqa: F401
+from .ops import (FFPlan, FF_AUTO, FF_EXACT, FF_TC, cosine_scores, label_propagation, norm_mask, propagate_labels,  # noqa: F401
                   propagate_labels_batched, restrict_neighborhood, sinkhorn, sinkhorn_from_scores)
 
-__all__ = ["sinkhorn", "sinkhorn_from_scores", "restrict_neighborhood", "norm_mask", "label_propagation",
+__all__ = ["sinkhorn", "sinkhorn_from_scores", "cosine_scores", "restrict_neighborhood", "norm_mask", "label_propagation",
            "propagate_labels", "propagate_labels_batched", "FFPlan", "FF_AUTO", "FF_EXACT", "FF_TC", "install"]
 
 

@@ -29,6 +29,8 @@ _PROTOS = {
     "timet_launch_count": (C.c_int64, []),
     "timet_sinkhorn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "timet_sinkhorn": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "timet_cosine_scores_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "timet_cosine_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "timet_ff_workspace_bytes": (C.c_size_t, [C.POINTER(FFParams)]),
     "timet_ff_tc_supported": (C.c_int, [C.POINTER(FFParams)]),
     "timet_ff_prepare": (C.c_int, [C.POINTER(FFParams), _P, _P, C.c_size_t, _P]),

@@ -107,6 +107,27 @@ def _sinkhorn_launch(x, kind, eps, iters, world_size):
     return out
 
 
+@torch.no_grad()
+def cosine_scores(x: torch.Tensor, prototypes: torch.Tensor) -> torch.Tensor:
+    """No-grad form of TimeT.get_feature_prototype_similarity (time_tuning.py:130-141):
+    F.normalize(x, dim=-1) @ prototypes.t() for x [B, dh], prototypes [K, dh] -> float32 [B, K], on the tensor
+    cores with an fp16 hi/lo split (~1e-7 from the fp32 result).  Use torch for the branch that needs autograd."""
+    dev_in = x.device
+    xc = _to_cuda(x.detach()).float().contiguous()
+    pc = _to_cuda(prototypes.detach()).float().contiguous()
+    B, dh = xc.shape
+    K = pc.shape[0]
+    if pc.shape[1] != dh:
+        raise ValueError(f"feature dim {dh} != prototype dim {pc.shape[1]}")
+    lib = _cabi.lib()
+    with torch.cuda.device(xc.device):
+        out = torch.empty((B, K), dtype=torch.float32, device=xc.device)
+        nbytes = int(lib.timet_cosine_scores_workspace_bytes(B, K, dh))
+        ws = _workspace(nbytes, xc.device)
+        check(lib.timet_cosine_scores(_ptr(xc), _ptr(pc), B, K, dh, _ptr(out), _ptr(ws), nbytes, _stream()), "cosine_scores")
+    return out if dev_in.type == "cuda" else out.to(dev_in)
+
+
 # --------------------------------------------------------------------------- small routines
 def restrict_neighborhood(h: int, w: int, size_mask_neighborhood: int) -> torch.Tensor:
     """Drop-in for mask_propagation.restrict_neighborhood: float32 [h*w, h*w] 0/1 mask (built on

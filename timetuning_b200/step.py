@@ -2,7 +2,7 @@
 CUDA path: the unit of work bench.py times and smoke() checks.
 
     (head feats of frame 0 and -1, backbone feats, prototypes)
-        -> cosine scores (torch: library GEMM, needs autograd in training — SURVEY.md §2.2 X1)
+        -> cosine scores (tensor-core fp16 hi/lo split GEMM, no-grad branch; the autograd branch stays in torch)
         -> Sinkhorn x2 (fused exp, one pass per iteration)
         -> batched Feature-Forwarding of Q_source over every clip
         -> (Q_source, Q_target, last-frame hard labels)
@@ -21,8 +21,8 @@ def ff_sinkhorn_step(head_src, head_tgt, backbone, prototypes, n_last_frames=7, 
     """head_src/head_tgt [bs, N, dh], backbone [bs, fs, N, D], prototypes [K, dh] — CUDA float32.
     Returns (batch_q [bs,N,K], target_q [bs,N,K], hard int64 [bs,sr,sr], labels [bs,fs,N,K])."""
     bs, N, dh = head_src.shape
-    scores_src = F.normalize(head_src.reshape(bs * N, dh), dim=-1, p=2) @ prototypes.t()     # :136-140
-    scores_tgt = F.normalize(head_tgt.reshape(bs * N, dh), dim=-1, p=2) @ prototypes.t()
+    scores_src = ops.cosine_scores(head_src.reshape(bs * N, dh), prototypes)                  # :136-140 (no-grad branch)
+    scores_tgt = ops.cosine_scores(head_tgt.reshape(bs * N, dh), prototypes)
     q_src = ops.sinkhorn_from_scores(scores_src, epsilon, sinkhorn_iterations, world_size)   # :164-165
     q_tgt = ops.sinkhorn_from_scores(scores_tgt, epsilon, sinkhorn_iterations, world_size)
     K = q_src.shape[1]
@@ -70,7 +70,7 @@ class HostStepPipeline:
                 self.d_backbone[c * cb:(c + 1) * cb].copy_(backbone[c * cb:(c + 1) * cb], non_blocking=True)
                 self.ev_chunk[c].record(self.copy_stream)
         main.wait_event(self.ev_head)
-        scores = F.normalize(self.d_head.reshape(2 * bs * N, self.dh), dim=-1, p=2) @ prototypes.t()
+        scores = ops.cosine_scores(self.d_head.reshape(2 * bs * N, self.dh), prototypes)
         q_src = ops.sinkhorn_from_scores(scores[:bs * N], epsilon, sinkhorn_iterations, world_size)
         q_tgt = ops.sinkhorn_from_scores(scores[bs * N:], epsilon, sinkhorn_iterations, world_size)
         self.labels[:, 0] = q_src.view(bs, N, K)
