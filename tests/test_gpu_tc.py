@@ -34,6 +34,7 @@ def ctx_frames(t, n_last):
     (14, 64, 3, 6, [0, 1, 2]),
     (60, 384, 3, 12, [0, 15, 29, 59]),
     (20, 96, 4, 4, [0, 3, 11]),
+    (28, 768, 3, 6, [0, 5, 13]),          # ViT-B width: streamed query tile
 ])
 def test_tc_raw_accumulators(sr, D, fs, radius, tile_ids):
     n_clips, C_, n_last, topk = 1, 8, 7, 5
@@ -89,6 +90,8 @@ def test_tc_raw_accumulators(sr, D, fs, radius, tile_ids):
     (20, 96, 9, 3, 4, 7, 2),         # FIFO eviction
     (16, 70, 5, 7, 3, 2, 2),         # padded dim
     (12, 64, 4, 7, 12, 5, 1),        # window = whole frame
+    (28, 768, 4, 7, 6, 5, 2),        # ViT-B width (streamed query tile)
+    (56, 768, 3, 7, 6, 5, 1),        # config 5 grid (ViT-B/8 448^2)
 ])
 def test_tc_engine_is_bit_identical_to_exact(sr, D, fs, n_last, radius, topk, bs):
     N = sr * sr

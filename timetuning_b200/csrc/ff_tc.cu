@@ -38,11 +38,14 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
              int64_t tile_override, float *__restrict__ dump, unsigned long long *__restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
     // carve: [A: NKC x 16 KB][B: nstages x NT*128][lists: 4 x 32 x 128 u32][ctl]; 1024-aligned for SWIZZLE_128B
+    // (streamed-A variant for Dp > 384: no resident A, every ring stage is [A chunk 16 KB | B chunk])
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     const uint32_t b_stage_bytes = (uint32_t)G.NT * 128u;
-    uint8_t *sB = sA + (size_t)G.NKC * 16384;
-    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * b_stage_bytes);
+    const uint32_t a_in_stage = G.a_resident ? 0u : 16384u;
+    const uint32_t stage_bytes = b_stage_bytes + a_in_stage;
+    uint8_t *sB = sA + (G.a_resident ? (size_t)G.NKC * 16384 : 0);   // ring base
+    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * stage_bytes);
     TcSmemCtl *ctl = reinterpret_cast<TcSmemCtl *>(sList + TC_GROUPS * TC_CAP * 128);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,8 +105,10 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
-            ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
-            for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, q_row0, &ctl->a_full);
+            if (G.a_resident) {
+                ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
+                for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, q_row0, &ctl->a_full);
+            }
             uint32_t stage = 0, phase = 0;                     // ring position without divisions
             for (int ci = 0; ci < nctx; ++ci) {
                 const int f = ctx_frame(t, G.n_last, ci);
@@ -111,8 +116,10 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     const int k_row0 = (int)(clip_row0 + (int64_t)f * G.N + (kr_lo + ch * G.RPC) * G.W);
                     for (int kc = 0; kc < G.NKC; ++kc) {
                         ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
-                        ptx::mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
-                        ptx::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, kc * 64, k_row0, &ctl->full[stage]);
+                        ptx::mbar_expect_tx(&ctl->full[stage], stage_bytes);
+                        uint8_t *st = sB + (size_t)stage * stage_bytes;
+                        if (!G.a_resident) ptx::tma_load_2d(st, &map_a, kc * 64, q_row0, &ctl->full[stage]);
+                        ptx::tma_load_2d(st + a_in_stage, &map_b, kc * 64, k_row0, &ctl->full[stage]);
                         if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -121,13 +128,13 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         if (lane == 0) {
-            ptx::mbar_wait(&ctl->a_full, 0);
+            if (G.a_resident) ptx::mbar_wait(&ctl->a_full, 0);
             ptx::tc_fence_after();
             stamp(2);
             // the issuing thread is on the critical path of every MMA: descriptors are built once and advanced by
             // adding to the 14-bit start-address field; the ring position is tracked without divisions
             const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sA)), db0 = ptx::umma_desc_sw128(ptx::smem_u32(sB));
-            const uint32_t stage_step = b_stage_bytes >> 4;
+            const uint32_t stage_step = stage_bytes >> 4, a_step = a_in_stage >> 4;
             uint32_t stage = 0, phase = 0, buf = 0, use = 0;
             int ch = 0;
             for (int tile = 0; tile < ntiles; ++tile) {
@@ -141,11 +148,13 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                 for (int kc = 0; kc < G.NKC; ++kc, da += 16384 >> 4) {
                     ptx::mbar_wait(&ctl->full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t db = db0 + (uint64_t)(stage * stage_step);
-                    ptx::umma_f16(d_tmem, da, db, idesc, kc != 0);
-                    ptx::umma_f16(d_tmem, da + 2, db + 2, idesc, true);      // +32 B per K = 16 step
-                    ptx::umma_f16(d_tmem, da + 4, db + 4, idesc, true);
-                    ptx::umma_f16(d_tmem, da + 6, db + 6, idesc, true);
+                    const uint64_t ds = db0 + (uint64_t)(stage * stage_step);
+                    const uint64_t db = ds + a_step;
+                    const uint64_t dq = G.a_resident ? da : ds;              // streamed A: the chunk sits in front of B
+                    ptx::umma_f16(d_tmem, dq, db, idesc, kc != 0);
+                    ptx::umma_f16(d_tmem, dq + 2, db + 2, idesc, true);      // +32 B per K = 16 step
+                    ptx::umma_f16(d_tmem, dq + 4, db + 4, idesc, true);
+                    ptx::umma_f16(d_tmem, dq + 6, db + 6, idesc, true);
                     ptx::umma_commit(&ctl->empty[stage]);          // frees the smem stage when the MMAs retire
                     if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                 }
@@ -411,14 +420,16 @@ int tc_make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int box_
 }
 
 size_t tc_smem_bytes(const TcGeom &G) {
-    return 1024 + (size_t)G.NKC * 16384 + (size_t)G.nstages * G.NT * 128 + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(TcSmemCtl) + 64;
+    const size_t a_res = G.a_resident ? (size_t)G.NKC * 16384 : 0, a_stage = G.a_resident ? 0 : 16384;
+    return 1024 + a_res + (size_t)G.nstages * ((size_t)G.NT * 128 + a_stage) + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(TcSmemCtl) + 64;
 }
 
 bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
     const int W = p.grid_w, H = p.grid_h;
     if (p.radius < 1 || p.radius > 15) return false;
     if (p.n_last_frames > 7 || p.topk > 8) return false;   // 3-bit context slot in the packed candidate; k + ties must fit 16 slots
-    if (W > 128 || L.Dp > 64 * TC_MAX_NKC) return false;
+    if (W > 128 || L.Dp > 64 * TC_MAX_NKC_STREAM) return false;
+    G->a_resident = (L.Dp <= 64 * TC_MAX_NKC) ? 1 : 0;
     int g = W, b = 16;
     while (b) { const int tmp = g % b; g = b; b = tmp; }   // gcd(W, 16)
     const int qrows = 16 / g;

@@ -371,7 +371,7 @@ int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *
     PairGeom PG;
     if (!tc_geometry(p, L, &PG.g)) return TIMET_ERR_UNSUPPORTED;
     TcGeom &G = PG.g;
-    if ((G.NT / 2) % 8 != 0) return TIMET_ERR_UNSUPPORTED;
+    if ((G.NT / 2) % 8 != 0 || !G.a_resident) return TIMET_ERR_UNSUPPORTED;
     G.nstages = TC_MAX_STAGES;
     const char *ns = getenv("TIMET_TC_STAGES");
     if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G.nstages = atoi(ns);

@@ -11,6 +11,7 @@ constexpr int TC_GROUPS = 4;                    // epilogue warpgroups (4 warps 
 constexpr int TC_THREADS = 128 + TC_GROUPS * 128;
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_NKC = 6;                  // resident query tile: Dp <= 384
+constexpr int TC_MAX_NKC_STREAM = 32;          // streamed query tile (A chunk re-loaded with every B chunk): Dp <= 2048
 constexpr int TC_CLIP_GROUP = 8;                // clips whose tiles are launched together (L2 locality)
 constexpr int TC_CAP = FF_CAND_CAP;            // 32 candidates per (query, epilogue group)
 constexpr float FF_TC_DELTA = 1.05e-3f;        // bound on |sim~ - sim|: fp16 RN of both unit vectors (2^-10) + fp32 accumulation
@@ -19,6 +20,7 @@ constexpr float TC_FIX_BIAS = 66.0f;           // sim~ + 2 in [1,3] lands in [64
 
 struct TcGeom {
     int H, W, N, Dp, NKC;
+    int a_resident;           // 1: query tile A stays in smem (Dp <= 384); 0: its 64-wide chunks ride in the ring stages
     int QR, tiles_per_frame;
     int RPC, NT, qrows;
     int n_clips, n_frames, nT, t_begin, n_last, radius, topk;
