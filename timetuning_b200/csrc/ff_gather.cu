@@ -46,19 +46,22 @@ __device__ __forceinline__ void ga_fma(float4 &a, float w, const float4 l) {
 // broadcast by shuffle; every lane then owns channel vectors c = lane, lane+32, ... and issues the <= 4 gathered
 // row loads of a batch back to back (coherent L2 loads: earlier frames were written by other CTAs of this
 // launch).  The next query's sparse row is prefetched while the current one is gathered.
-template <typename V>
+// CLUSTER = false: the same body for ONE target frame per launch with `vcs` plain CTAs per clip (few clips: a
+// cluster of 8 CTAs per clip would leave most SMs idle; frames then cost one launch each).
+template <typename V, bool CLUSTER>
 __global__ void __launch_bounds__(GA_THREADS, 2)
 ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const float *__restrict__ sel_w,
                  const int32_t *__restrict__ sel_k, const int32_t *__restrict__ sel_cnt, int n_frames, int N, int C,
-                 int nT, int kw, int t_begin) {
-    const unsigned cs = cluster_nctarank(), cr = cluster_ctarank();
+                 int nT, int kw, int t_begin, int t_first, int t_last, int vcs) {
+    const unsigned cs = CLUSTER ? cluster_nctarank() : (unsigned)vcs;
+    const unsigned cr = CLUSTER ? cluster_ctarank() : (blockIdx.x % (unsigned)vcs);
     const int clip = blockIdx.x / cs;
     constexpr int VW = sizeof(V) / sizeof(float);
     const int CV = C / VW;
     const int lane = threadIdx.x & 31;
     const int wid = cr * GA_WARPS + (threadIdx.x >> 5), nw = cs * GA_WARPS;
     float *clip_base = labels + (int64_t)clip * n_frames * N * C;
-    for (int t = t_begin; t < n_frames; ++t) {
+    for (int t = t_first; t <= t_last; ++t) {
         const int64_t q0 = ((int64_t)clip * nT + (t - t_begin)) * N;
         int i = wid;
         int cnt = 0;
@@ -105,9 +108,9 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
             }
             i = inext; cnt = cnt_n; w_l = w_n; k_l = k_n;
         }
-        cluster_barrier();
+        if (CLUSTER) cluster_barrier();
     }
-    if (hard) {   // argmax over channels of the last frame, lowest index on ties (time_tuning.py:296)
+    if (hard && t_last == n_frames - 1) {   // argmax over channels of the last frame, lowest index on ties (time_tuning.py:296)
         for (int i = wid; i < N; i += nw) {
             const float *row = clip_base + ((int64_t)(n_frames - 1) * N + i) * C;
             float best = -INFINITY;
@@ -132,28 +135,46 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
     const int32_t *sel_k = reinterpret_cast<const int32_t *>(ws + L.off_sel_k);
     const int32_t *sel_cnt = reinterpret_cast<const int32_t *>(ws + L.off_sel_cnt);
     const bool vec = (p.n_channels % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0);
-    // cluster size: as many CTAs per clip as useful (<= 8, power of two) without exceeding ~2 CTAs per SM in total
-    int cs = 8;
-    while (cs > 1 && ((int64_t)p.n_clips * cs > 2 * (int64_t)num_sms() || (int64_t)L.N < (int64_t)cs * GA_WARPS)) cs >>= 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(p.n_clips * cs));
-    cfg.blockDim = dim3(GA_THREADS);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (vec)
-        TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4>, labels, hard, sel_w, sel_k, sel_cnt, (int)p.n_frames,
-                                      L.N, (int)p.n_channels, L.nT, L.kw, (int)p.t_begin));
-    else
-        TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float>, labels, hard, sel_w, sel_k, sel_cnt, (int)p.n_frames,
-                                      L.N, (int)p.n_channels, L.nT, L.kw, (int)p.t_begin));
-    TIMET_LAUNCHED();
+    const int nfr = p.n_frames, nch = p.n_channels, tb = p.t_begin;
+    if ((int64_t)p.n_clips * 8 >= num_sms() / 2) {
+        // cluster size: as many CTAs per clip as useful (<= 8, power of two) without exceeding ~2 CTAs per SM in total
+        int cs = 8;
+        while (cs > 1 && ((int64_t)p.n_clips * cs > 2 * (int64_t)num_sms() || (int64_t)L.N < (int64_t)cs * GA_WARPS)) cs >>= 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.n_clips * cs));
+        cfg.blockDim = dim3(GA_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (vec)
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4, true>, labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+                                          L.nT, L.kw, tb, tb, nfr - 1, cs));
+        else
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float, true>, labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+                                          L.nT, L.kw, tb, tb, nfr - 1, cs));
+        TIMET_LAUNCHED();
+        return TIMET_OK;
+    }
+    // few clips: one launch per target frame, every SM busy
+    int vcs = (int)((2 * (int64_t)num_sms() + p.n_clips - 1) / p.n_clips);
+    const int max_useful = (L.N + GA_WARPS - 1) / GA_WARPS;
+    if (vcs > max_useful) vcs = max_useful;
+    if (vcs < 1) vcs = 1;
+    for (int t = tb; t < nfr; ++t) {
+        if (vec)
+            ff_gather_kernel<float4, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+                                                                                  L.nT, L.kw, tb, t, t, vcs);
+        else
+            ff_gather_kernel<float, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+                                                                                 L.nT, L.kw, tb, t, t, vcs);
+        TIMET_LAUNCHED();
+    }
     return TIMET_OK;
 }
 

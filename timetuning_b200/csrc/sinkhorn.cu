@@ -243,6 +243,7 @@ __global__ void sk_fill(float *p, int n, float v) {
 // (bit-reproducible, identical on every CTA).
 constexpr int SKR_THREADS = 1024;
 constexpr int SKR_WARPS = SKR_THREADS / 32;
+constexpr int SKR_RED = 8;            // rows of the cross-warp reduction scratch (warps fold in SKR_WARPS / SKR_RED rounds)
 
 struct SkResArgs {
     const float *in;
@@ -268,13 +269,34 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int tar
     __syncthreads();
 }
 
+// Deterministic cross-warp sum of per-lane column partials: warps fold into SKR_RED scratch rows in
+// SKR_WARPS / SKR_RED ordered rounds; afterwards column i = sum of red[0..SKR_RED) [i].
+template <int NV4>
+__device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[NV4], int K, int K4, int warp, int lane) {
+    for (int round = 0; round < SKR_WARPS / SKR_RED; ++round) {
+        if ((warp / SKR_RED) == round) {
+            float4 *dst = reinterpret_cast<float4 *>(red + (warp % SKR_RED) * K);
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                const int i4 = lane + 32 * v;
+                if (i4 < K4) {
+                    float4 a = acc[v];
+                    if (round > 0) { const float4 o = dst[i4]; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+                    dst[i4] = a;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int NV4>
 __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
     extern __shared__ float4 smem4[];
     const int K = A.K, K4 = K >> 2;
     float4 *E = smem4;                                                   // [rows_per_cta, K4]
     float *a_s = reinterpret_cast<float *>(smem4 + (size_t)A.rows_per_cta * K4);    // [K]
-    float *red = a_s + K;                                                // [SKR_WARPS, K]
+    float *red = a_s + K;                                                // [SKR_RED, K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_cta;
     const int nrows = (int)max((int64_t)0, min((int64_t)A.rows_per_cta, A.B - row0));
@@ -303,16 +325,11 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
     }
 
     // ---- R^(0) = column sums of E: per-CTA float partials, grid barrier, fixed-order fold -> a_i = r / R_i
-#pragma unroll
-    for (int v = 0; v < NV4; ++v) {
-        const int i4 = lane + 32 * v;
-        if (i4 < K4) reinterpret_cast<float4 *>(red + warp * K)[i4] = acc[v];
-    }
-    __syncthreads();
+    skr_fold_warps<NV4>(red, acc, K, K4, warp, lane);
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < SKR_WARPS; ++w) t += red[w * K + i];
+        for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
         A.partials[(size_t)blockIdx.x * K + i] = t;
     }
     grid_barrier(A.bar, (++epoch) * gridDim.x);
@@ -359,17 +376,12 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
         if (last) break;
         // ---- marginals of Q itself, u_i = sum_j a_i E_ji b_j (they sum to 1 over i, so 2^-62 fixed point never
         // overflows): integer atomics are associative -> the grid-wide sum is bit-reproducible without a fold.
-#pragma unroll
-        for (int v = 0; v < NV4; ++v) {
-            const int i4 = lane + 32 * v;
-            if (i4 < K4) reinterpret_cast<float4 *>(red + warp * K)[i4] = acc[v];
-        }
-        __syncthreads();
+        skr_fold_warps<NV4>(red, acc, K, K4, warp, lane);
         unsigned long long *ufix = A.ufix + (size_t)(it % 3) * K;
         for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
             float t = 0.f;
 #pragma unroll
-            for (int w = 0; w < SKR_WARPS; ++w) t += red[w * K + i];
+            for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
             atomicAdd(ufix + i, (unsigned long long)__float2ll_rn(t * 4611686018427387904.0f));
         }
         grid_barrier(A.bar, (++epoch) * gridDim.x);
@@ -389,8 +401,8 @@ static bool sk_resident_plan(int64_t B, int K, int *grid, int *rows_per_cta, siz
     if (K % 4 != 0 || K > 128 * SK_MAX_V4) return false;
     const int g = num_sms();
     const int64_t rpc = (B + g - 1) / g;
-    const size_t need = (size_t)rpc * K * 4 + (size_t)K * 4 + (size_t)SKR_WARPS * K * 4;
-    if (need > 220 * 1024) return false;
+    const size_t need = (size_t)rpc * K * 4 + (size_t)K * 4 + (size_t)SKR_RED * K * 4;
+    if (need > 226 * 1024) return false;
     *grid = (int)((B + rpc - 1) / rpc);
     *rows_per_cta = (int)rpc;
     *smem = need;
