@@ -201,6 +201,7 @@ def main():
     hard = torch.empty((bs, N), dtype=torch.int64, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     stage_ev = []
+    tc_events = [] if engine_used == "tcgen05" else None
 
     def step(x_hs, x_ht, x_bb, record=False):
         """staged form of timetuning_b200.step.ff_sinkhorn_step so the selection kernel can be timed live"""
@@ -216,7 +217,13 @@ def main():
         if record: e[2].record()
         plan.prepare(x_bb)
         if record: e[3].record()
-        plan.select(engine)
+        if record and tc_events is not None:
+            eb, ee = ev(), ev()
+            eb.record(); ee.record()                    # materialise the cudaEvent_t handles
+            plan.select_timed(engine, eb, ee)           # the library re-records them around the tcgen05 kernel
+            tc_events.append((eb, ee))
+        else:
+            plan.select(engine)
         if record: e[4].record()
         plan.gather(labels, hard)
         if record:
@@ -288,16 +295,27 @@ def main():
             pass
         sigma_ctx = sum(1 + (t - max(1, t - CFG["n_last"])) for t in range(1, fs))
         dense_flops = 2.0 * N * N * D * sigma_ctx * bs                        # SURVEY.md §8d, per launch (per GPU)
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
         if engine_used == "tcgen05":
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            roof = {"bound": "tensor", "kernel": "ff_select (tcgen05 affinity + fused window/top-k nomination)",
-                    "achieved": dense_flops / (stage_ms["select"] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                    "flops_model": "dense 2*N^2*D*sum_ctx per clip (SURVEY.md §8d)", "traffic": None}
+            tc_ms = sum(a.elapsed_time(b) for a, b in tc_events) / len(tc_events)
+            stage_ms["select_tc_kernel"] = tc_ms
+            # executed = key tiles actually multiplied (window band only), M padded to 128 rows
+            QR, RPC, W_ = 128 // sr, (256 // sr) // (16 // __import__("math").gcd(sr, 16)) * (16 // __import__("math").gcd(sr, 16)), sr
+            exec_flops = 0.0
+            for qt in range(-(-sr // QR)):
+                qr0, qr1 = qt * QR, min(sr - 1, qt * QR + QR - 1)
+                rows = min(sr - 1, qr1 + CFG["radius"]) - max(0, qr0 - CFG["radius"]) + 1
+                exec_flops += 2.0 * 128 * rows * W_ * D
+            exec_flops *= sigma_ctx * bs
+            roof = {"bound": "tensor", "kernel": "ff_tc_kernel (tcgen05 affinity + fused window / top-k nomination), "
+                    "timed alone with CUDA events recorded by the library around its launch",
+                    "achieved": dense_flops / (tc_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
+                    "flops_model": "dense 2*N^2*D*sum_ctx per clip (SURVEY.md §8d) x clips per launch",
+                    "executed_tflops": exec_flops / (tc_ms * 1e-3) / 1e12, "executed_over_dense": exec_flops / dense_flops,
+                    "ms_per_launch": tc_ms,
+                    "traffic": 162.8e6, "traffic_source": "ncu --set full, profiles/r1_ncu_full_kernels.md: dram read 154.2 MB + write 8.6 MB per launch"}
         else:
-            # exact fp32 engine: CUDA-core bound; report against the fp32 FMA peak is meaningless for the
-            # north star, so the dense-equivalent tensor figure is reported for continuity
-            peak = peaks.get("bf16_tflops_sustained", 1400.0)
             roof = {"bound": "tensor", "kernel": "ff_select_exact (fp32 CUDA-core scan; tensor-core engine not used)",
                     "achieved": dense_flops / (stage_ms["select"] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
@@ -309,7 +327,8 @@ def main():
         prep_bytes = bs * fs * N * (D * 4 + D * 6)
         extra = {
             "sinkhorn": {"bound": "hbm", "achieved": sk_bytes / (stage_ms["sinkhorn_x2"] * 1e-3) / 1e9, "peak": hbm,
-                         "unit": "GB/s", "bytes_model": "(iters+2)*B*K*4 per call, 2 calls"},
+                         "unit": "GB/s", "bytes_model": "(iters+2)*B*K*4 per call, 2 calls (streaming model, SURVEY.md §8d); the "
+                         "resident kernel's real DRAM traffic is the compulsory 2*B*K*4"},
             "gather": {"bound": "hbm", "achieved": gather_bytes / (stage_ms["gather"] * 1e-3) / 1e9, "peak": hbm,
                        "unit": "GB/s", "bytes_model": "compulsory (fs-1)*N*C*4 write + N*C*4 read per clip"},
             "prepare": {"bound": "hbm", "achieved": prep_bytes / (stage_ms["prepare"] * 1e-3) / 1e9, "peak": hbm,

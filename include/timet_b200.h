@@ -122,6 +122,10 @@ int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspa
  * contexts with ties kept, normalised weights (:422-436) -> sparse (weight, key) lists in the workspace */
 int timet_ff_select(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
                     timet_stream_t stream);
+/* timet_ff_select with two caller-created cudaEvent_t (may be NULL) recorded on `stream` immediately before and
+ * after the tensor-core nomination kernel: lets a caller time the dominant kernel alone without a profiler. */
+int timet_ff_select_timed(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+                          timet_stream_t stream, void *event_before_nominate, void *event_after_nominate);
 /* stage 3: frame-sequential weighted gather of the context labels (:439-444) and argmax */
 int timet_ff_gather(const timet_ff_params *p, float *labels, int64_t *hard, const void *workspace,
                     size_t workspace_bytes, timet_stream_t stream);

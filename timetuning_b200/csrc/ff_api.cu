@@ -3,6 +3,8 @@
 
 namespace timet {
 
+extern thread_local cudaEvent_t g_ev_nominate_begin, g_ev_nominate_end;
+
 __global__ void ff_export_kernel(const float *sel_w, const int32_t *sel_k, const int32_t *sel_cnt, int64_t q0, int N,
                                  int kw, float *w_out, int32_t *k_out, int32_t *c_out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,6 +147,17 @@ int timet_debug_tc_trace(const timet_ff_params *p, const void *workspace, size_t
     if (rc != TIMET_OK) return rc;
     TIMET_CHECK_ARG(out != nullptr, "debug_tc_trace: out is NULL");
     return ff_tc_debug_trace(*p, L, (const char *)workspace, (unsigned long long *)out, n_ctas, (cudaStream_t)stream);
+}
+
+
+int timet_ff_select_timed(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+                          timet_stream_t stream, void *event_before_nominate, void *event_after_nominate) {
+    g_ev_nominate_begin = (cudaEvent_t)event_before_nominate;
+    g_ev_nominate_end = (cudaEvent_t)event_after_nominate;
+    const int rc = timet_ff_select(p, engine, workspace, workspace_bytes, stream);
+    g_ev_nominate_begin = nullptr;
+    g_ev_nominate_end = nullptr;
+    return rc;
 }
 
 }

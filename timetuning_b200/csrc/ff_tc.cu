@@ -475,6 +475,10 @@ int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, c
 
 int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
 
+// optional CUDA events recorded on the stream right before / after the nomination (tensor-core) kernel, so a
+// caller can time the dominant kernel alone (bench.py roofline); set through timet_ff_select_timed
+thread_local cudaEvent_t g_ev_nominate_begin = nullptr, g_ev_nominate_end = nullptr;
+
 int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
     TcGeom G;
     if (!tc_geometry(p, L, &G)) {
@@ -484,6 +488,7 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
     int rc;
     uint32_t *cand = reinterpret_cast<uint32_t *>(ws + L.off_cand);
     uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_cand_meta);
+    if (g_ev_nominate_begin) TIMET_CUDA(cudaEventRecord(g_ev_nominate_begin, st));
     // nomination: 1-CTA kernel by default; TIMET_TC_PAIR=1 selects the CTA-pair kernel (cta_group::2, ff_tc2.cu)
     const char *pe = getenv("TIMET_TC_PAIR");
     rc = (pe && pe[0] == '1') ? ff_select_tc_pair_launch(p, L, ws, st) : TIMET_ERR_UNSUPPORTED;   // opt-in
@@ -502,6 +507,7 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
         TIMET_LAUNCHED();
     }
 
+    if (g_ev_nominate_end) TIMET_CUDA(cudaEventRecord(g_ev_nominate_end, st));
     unsigned int *redo_count = reinterpret_cast<unsigned int *>(ws + L.off_redo);
     int32_t *redo_list = reinterpret_cast<int32_t *>(ws + L.off_redo + 256);
     const size_t fsmem = (size_t)FIN_WARPS * L.Dp * sizeof(float);

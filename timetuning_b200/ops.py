@@ -198,6 +198,14 @@ class FFPlan:
             check(_cabi.lib().timet_ff_select(C.byref(self.params), int(engine), _ptr(self.workspace), self.nbytes,
                                               _stream()), "ff_select")
 
+    def select_timed(self, engine, ev_begin, ev_end):
+        """select() with two torch.cuda.Event(enable_timing=True) recorded by the library right around the
+        tensor-core nomination kernel (they must have been recorded once before so that their handles exist)."""
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_select_timed(C.byref(self.params), int(engine), _ptr(self.workspace), self.nbytes,
+                                                    _stream(), C.c_void_p(ev_begin.cuda_event), C.c_void_p(ev_end.cuda_event)),
+                  "ff_select_timed")
+
     def gather(self, labels, hard=None):
         with torch.cuda.device(self.device):
             check(_cabi.lib().timet_ff_gather(C.byref(self.params), _ptr(labels), _ptr(hard), _ptr(self.workspace),
