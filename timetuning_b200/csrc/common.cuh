@@ -47,16 +47,14 @@ int num_sms();
 // ------------------------------------------------------------------ FF workspace layout
 constexpr int FF_CAND_CAP = 32;     // in-kernel candidate list capacity per (query, epilogue group)
 constexpr int FF_CAND_STORE = 16;   // candidates published per query after the merged final compaction
-constexpr int FF_LIST_SLOTS = 32;   // in-register sorted list = one warp
 constexpr int FF_TRACE_CTAS = 4096;  // debug timeline (env TIMET_TC_TRACE): first CTAs x 8 globaltimer stamps
 constexpr int FF_TRACE_SLOTS = 8;
-constexpr int FF_SCRATCH_SMS = 192; // >= %nsmid on every B200 SKU (160 physical SMs)
 
 struct FFLayout {
     int N, Dp, nT, kw;               // patches, padded dim (multiple of 64), target frames, slots per query
     int64_t rows;                    // n_clips * n_frames * N feature rows
     int64_t queries;                 // n_clips * nT * N
-    size_t off_fn32, off_fn16, off_sel_w, off_sel_k, off_sel_cnt, off_cand, off_cand_meta, off_stats, off_redo, off_scratch, off_trace;
+    size_t off_fn32, off_fn16, off_sel_w, off_sel_k, off_sel_cnt, off_cand, off_cand_meta, off_stats, off_redo, off_trace;
     size_t total;
 };
 
@@ -81,8 +79,6 @@ static inline FFLayout ff_layout(const timet_ff_params &p) {
     L.off_cand_meta = o; o = align_up(o + (size_t)L.queries * sizeof(uint32_t), 1024);
     L.off_stats = o; o = align_up(o + 8 * sizeof(int64_t), 1024);
     L.off_redo = o; o = align_up(o + 256 + (size_t)L.queries * sizeof(int32_t), 1024);   // count header + query ids
-    // per-SM candidate lists of the tensor-core kernel: FF_SCRATCH_SMS x 4 groups x 128 queries x 32 slots (u32)
-    L.off_scratch = o; o = align_up(o + (size_t)FF_SCRATCH_SMS * 4 * 128 * FF_CAND_CAP * sizeof(uint32_t), 1024);
     L.off_trace = o; o = align_up(o + (size_t)FF_TRACE_CTAS * FF_TRACE_SLOTS * sizeof(unsigned long long), 1024);
     L.total = o;
     return L;

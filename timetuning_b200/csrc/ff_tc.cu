@@ -9,21 +9,26 @@
 // FF_TC_DELTA).  The tensor cores only NOMINATE: a key is appended to the query's candidate list
 // when sim~ > thr, where thr is always (k-th largest sim~ seen so far) - 2*delta, a provable lower
 // bound of (final theta_i - delta).  Hence every key of the true top-k (ties included) is in the
-// list.  ff_finalize then re-evaluates the <= 64 candidates with the canonical fp32 dot product
+// list.  ff_finalize then re-evaluates the <= 16 candidates with the canonical fp32 dot product
 // (common.cuh) and applies the reference's selection exactly.  A query whose list overflowed is
 // re-done by the exact engine.  The result is bit-identical to TIMET_FF_EXACT by construction.
 //
-// One CTA per (clip, target frame, query tile of QR grid rows <= 128 queries):
-//   warp 0      TMA producer: query tile A (resident, Dp/64 swizzled 64-wide chunks) once, then a
-//               3-stage ring of key chunks B (NT = RPC*W keys x 64) for every context x key-row chunk
-//               that intersects the tile's window band (tiles outside the band are never loaded)
-//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=NT (<=256), K=16, fp32
-//               accumulators in TMEM, two 256-column buffers (ping-pong)
-//   warp 2      TMEM allocator
-//   warps 4-7   epilogue group 0 (even key tiles), warps 8-11 epilogue group 1 (odd key tiles):
-//               tcgen05.ld 32x32b, thread = query row; window test by index arithmetic; compare with
-//               the running threshold; append packed (sim~, ctx, drow, dcol) to a per-thread list in
-//               shared memory; warp-synchronous compaction raises the threshold.
+// One CTA (640 threads) per (clip, target frame, query tile of QR grid rows <= 128 queries):
+//   warp 0      TMA producer: query tile A (resident for Dp <= 384: Dp/64 swizzled 64-wide chunks loaded once;
+//               streamed with the key chunks for larger Dp), then a ring of key chunks B (NT = RPC*W keys x 64)
+//               for every context x key-row chunk that intersects the tile's window band (tiles outside the band
+//               are never loaded or multiplied)
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=NT (<=256), K=16, fp32 accumulators in
+//               TMEM (2 x 256 or 4 x 128 columns); descriptors advanced incrementally, no divisions on this path
+//   warp 2      TMEM allocator          warp 3   initialises the shared per-query thresholds
+//   warps 4-19  four epilogue groups of 4 warps (thread = query row = TMEM lane).  2 buffers: groups g, g+2 share
+//               the key tiles of buffer g & 1 and split their key rows by parity; 4 buffers: one group per buffer.
+//               tcgen05.ld 32x32b.x16; window test by index arithmetic; predicated append of packed
+//               (sim~, ctx, drow, dcol) candidates to a per-(query, group) list in shared memory; warp-synchronous
+//               single-pass compaction raises the nomination threshold, which the groups of a query share through
+//               an atomicMax word in shared memory; at the end the four lists are filtered with the final
+//               threshold, merged and <= 16 candidates per query are published.
+// ff_tc2.cu holds the CTA-pair (cta_group::2) variant of the same kernel.
 #include <stdlib.h>
 
 #include "ff_tc_dev.cuh"
@@ -34,8 +39,7 @@ namespace timet {
 template <bool DUMP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom G,
-             uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, uint32_t *__restrict__ scratch,
-             int64_t tile_override, float *__restrict__ dump, unsigned long long *__restrict__ trace) {
+             uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, int64_t tile_override, float *__restrict__ dump, unsigned long long *__restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
     // carve: [A: NKC x 16 KB][B: nstages x NT*128][lists: 4 x 32 x 128 u32][ctl]; 1024-aligned for SWIZZLE_128B
     // (streamed-A variant for Dp > 384: no resident A, every ring stage is [A chunk 16 KB | B chunk])
@@ -449,8 +453,6 @@ bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
     G->RPC = RPC; G->NT = RPC * W; G->qrows = qrows;
     G->n_clips = p.n_clips; G->n_frames = p.n_frames; G->nT = L.nT; G->t_begin = p.t_begin;
     G->n_last = p.n_last_frames; G->radius = p.radius; G->topk = p.topk;
-    const int side = 2 * p.radius + 1;
-    G->trig = 16; (void)side;
     const char *fl = getenv("TIMET_TC_FLAGS");
     G->flags = fl ? atoi(fl) : 0;
     const char *cg = getenv("TIMET_TC_CLIP_GROUP");
@@ -500,10 +502,9 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
         if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
         const size_t smem = tc_smem_bytes(G);
         TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        uint32_t *scratch = reinterpret_cast<uint32_t *>(ws + L.off_scratch);
         const char *tr = getenv("TIMET_TC_TRACE");
         unsigned long long *trace = (tr && tr[0] == '1') ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
-        ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, scratch, -1, nullptr, trace);
+        ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, -1, nullptr, trace);
         TIMET_LAUNCHED();
     }
 
@@ -540,7 +541,7 @@ int ff_tc_debug_tile(const timet_ff_params &p, const FFLayout &L, char *ws, int6
     if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
     const size_t smem = tc_smem_bytes(G);
     TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ff_tc_kernel<true><<<1, TC_THREADS, smem, st>>>(map_a, map_b, G, nullptr, nullptr, reinterpret_cast<uint32_t *>(ws + L.off_scratch), tile_id, dump, nullptr);
+    ff_tc_kernel<true><<<1, TC_THREADS, smem, st>>>(map_a, map_b, G, nullptr, nullptr, tile_id, dump, nullptr);
     TIMET_LAUNCHED();
     return TIMET_OK;
 }

@@ -25,7 +25,6 @@ struct TcGeom {
     int RPC, NT, qrows;
     int n_clips, n_frames, nT, t_begin, n_last, radius, topk;
     int nbuf, buf_cols, nstages;   // TMEM accumulator buffers (4 x 128 or 2 x 256 columns), B ring depth
-    int trig;                 // compaction trigger
     int clip_group;           // clips whose tiles are launched together (L2 locality); env TIMET_TC_CLIP_GROUP
     int flags;                // debug (env TIMET_TC_FLAGS): 1 = epilogue releases tiles unscanned, 2 = scan but never append
     int64_t total_tiles;

@@ -259,8 +259,8 @@ struct SkResArgs {
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        // release at gpu scope: cumulative over everything the CTA wrote before the bar.sync above
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned int v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
