@@ -172,6 +172,13 @@ int timet_norm_mask(const void *mask, void *out, int n_channels, int64_t hw, int
 int timet_comm_unique_id(void *id_out);
 int timet_comm_init(const void *id, int rank, int world_size, timet_comm_t *comm_out);
 int timet_comm_destroy(timet_comm_t comm);
+/* Optional NVLink peer-memory path for the Sinkhorn marginals (single node): every rank exports a small exchange
+ * buffer through CUDA IPC (timet_comm_p2p_handle -> 64 bytes), the host side all-gathers the handles, and
+ * timet_comm_p2p_connect maps the peers' buffers.  With it, timet_sinkhorn(world_size > 1) runs as ONE resident
+ * kernel per call that exchanges the K-vector by direct peer stores + flags (no NCCL launch per iteration). */
+#define TIMET_IPC_HANDLE_BYTES 64
+int timet_comm_p2p_handle(timet_comm_t comm, void *handle_out);
+int timet_comm_p2p_connect(timet_comm_t comm, const void *all_handles /* world_size x 64 bytes, rank order */);
 /* sum-all-reduce of n float32 in place on `stream` (exposed for tests of the plumbing) */
 int timet_comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, timet_stream_t stream);
 

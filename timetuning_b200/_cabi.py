@@ -47,6 +47,8 @@ _PROTOS = {
     "timet_norm_mask": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P]),
     "timet_comm_unique_id": (C.c_int, [_P]),
     "timet_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "timet_comm_p2p_handle": (C.c_int, [_P, _P]),
+    "timet_comm_p2p_connect": (C.c_int, [_P, _P]),
     "timet_comm_destroy": (C.c_int, [_P]),
     "timet_comm_allreduce_f32": (C.c_int, [_P, _P, C.c_int64, _P]),
 }
@@ -55,6 +57,7 @@ EXPORTS = tuple(_PROTOS)
 SK_EXP, SK_SCORES = 0, 1
 FF_EXACT, FF_TC, FF_AUTO = 0, 1, 2
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 def lib():

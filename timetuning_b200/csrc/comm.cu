@@ -53,6 +53,12 @@ static NcclApi *nccl() {
 struct Comm {
     ncclComm_t nccl;
     int rank, world_size;
+    // peer-memory exchange (NVLink P2P through CUDA IPC) used by the resident Sinkhorn kernel
+    void *p2p_local = nullptr;                 // this rank's P2PBuf (cudaMalloc'ed here, written by the peers)
+    void *p2p_peers_host[P2P_MAX_RANKS] = {};   // device pointers of every rank's P2PBuf (own at [rank])
+    void **p2p_peers_dev = nullptr;            // the same table in device memory
+    unsigned long long p2p_epoch = 0;          // exchanges performed so far (identical on every rank)
+    bool p2p_ready = false;
 };
 
 #define TIMET_NCCL(call)                                                                          \
@@ -71,6 +77,13 @@ int comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, cudaStream_t st
     Comm *c = (Comm *)comm;
     TIMET_NCCL(api->AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, c->nccl, st));
     return TIMET_OK;
+}
+
+bool comm_p2p_info(timet_comm_t comm, void ***peers_dev, int *rank, int *ws, unsigned long long **epoch) {
+    Comm *c = (Comm *)comm;
+    if (!c || !c->p2p_ready) return false;
+    *peers_dev = c->p2p_peers_dev; *rank = c->rank; *ws = c->world_size; *epoch = &c->p2p_epoch;
+    return true;
 }
 
 }  // namespace timet
@@ -107,11 +120,51 @@ int timet_comm_init(const void *id, int rank, int world_size, timet_comm_t *comm
     return TIMET_OK;
 }
 
+int timet_comm_p2p_handle(timet_comm_t comm, void *handle_out) {
+    TIMET_CHECK_ARG(comm && handle_out, "comm_p2p_handle: NULL pointer");
+    Comm *c = (Comm *)comm;
+    TIMET_CHECK_ARG(c->world_size <= P2P_MAX_RANKS, "comm_p2p: world size %d > %d", c->world_size, P2P_MAX_RANKS);
+    if (!c->p2p_local) {
+        TIMET_CUDA(cudaMalloc(&c->p2p_local, sizeof(P2PBuf)));
+        TIMET_CUDA(cudaMemset(c->p2p_local, 0, sizeof(P2PBuf)));
+        TIMET_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    TIMET_CUDA(cudaIpcGetMemHandle(&h, c->p2p_local));
+    static_assert(sizeof(h) == TIMET_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &h, sizeof(h));
+    return TIMET_OK;
+}
+
+int timet_comm_p2p_connect(timet_comm_t comm, const void *all_handles) {
+    TIMET_CHECK_ARG(comm && all_handles, "comm_p2p_connect: NULL pointer");
+    Comm *c = (Comm *)comm;
+    TIMET_CHECK_ARG(c->p2p_local != nullptr, "comm_p2p_connect: call timet_comm_p2p_handle first");
+    for (int r = 0; r < c->world_size; ++r) {
+        if (r == c->rank) { c->p2p_peers_host[r] = c->p2p_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)all_handles + (size_t)r * TIMET_IPC_HANDLE_BYTES, sizeof(h));
+        TIMET_CUDA(cudaIpcOpenMemHandle(&c->p2p_peers_host[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    TIMET_CUDA(cudaMalloc((void **)&c->p2p_peers_dev, sizeof(void *) * P2P_MAX_RANKS));
+    TIMET_CUDA(cudaMemcpy(c->p2p_peers_dev, c->p2p_peers_host, sizeof(void *) * P2P_MAX_RANKS, cudaMemcpyHostToDevice));
+    c->p2p_epoch = 0;
+    c->p2p_ready = true;
+    return TIMET_OK;
+}
+
 int timet_comm_destroy(timet_comm_t comm) {
     if (!comm) return TIMET_OK;
     NcclApi *api = nccl();
     if (!api) return TIMET_ERR_NCCL;
     Comm *c = (Comm *)comm;
+    if (c->p2p_ready) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < c->world_size; ++r)
+            if (r != c->rank && c->p2p_peers_host[r]) cudaIpcCloseMemHandle(c->p2p_peers_host[r]);
+        cudaFree(c->p2p_peers_dev);
+    }
+    if (c->p2p_local) cudaFree(c->p2p_local);
     TIMET_NCCL(api->CommDestroy(c->nccl));
     delete c;
     return TIMET_OK;

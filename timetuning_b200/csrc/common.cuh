@@ -44,6 +44,16 @@ int64_t &launch_counter();
 
 int num_sms();
 
+// ------------------------------------------------------------------ peer-memory exchange buffer (one per rank)
+constexpr int P2P_MAX_RANKS = 16;
+constexpr int P2P_MAX_K = 1024;
+struct P2PBuf {
+    unsigned long long flag[P2P_MAX_RANKS];          // flag[src] = number of exchanges src has published here
+    unsigned long long pad[16];
+    float slot[3][P2P_MAX_RANKS][P2P_MAX_K];         // slot[e % 3][src] = src's K-vector of exchange e
+};
+bool comm_p2p_info(timet_comm_t comm, void ***peers_dev, int *rank, int *ws, unsigned long long **epoch);
+
 // ------------------------------------------------------------------ FF workspace layout
 constexpr int FF_CAND_CAP = 32;     // in-kernel candidate list capacity per (query, epilogue group)
 constexpr int FF_CAND_STORE = 16;   // candidates published per query after the merged final compaction

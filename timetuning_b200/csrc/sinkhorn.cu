@@ -251,6 +251,9 @@ struct SkResArgs {
     float *partials;          // [2, grid, K]
     unsigned int *bar;        // monotonic grid-barrier counter (zeroed before launch)
     unsigned long long *ufix; // [3, K] fixed-point marginal accumulators (zeroed before launch)
+    void *const *peers;       // world_size > 1: every rank's P2PBuf (NVLink peer memory), else nullptr
+    int rank, ws;
+    unsigned long long epoch0; // exchanges completed before this call (same on every rank)
     int64_t B;
     int K, iters, rows_per_cta, scores_mode;
     float inv_eps, r, c;
@@ -288,6 +291,45 @@ __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[N
         }
         __syncthreads();
     }
+}
+
+// Cross-GPU sum of a K-vector through NVLink peer memory (world_size > 1): CTA 0 stores this rank's vector into
+// slot[e % 3][rank] of EVERY rank's exchange buffer, then publishes flag[rank] = e + 1 with release semantics at
+// system scope; every CTA of every rank waits until all world_size flags of its own buffer reached e + 1 and adds
+// the world_size vectors in rank order (bit-identical on all ranks).  `vec` (shared memory, [K]) holds the local
+// vector on entry and the global sum on exit.  A slot is reused after 3 exchanges; a peer can only be one exchange
+// ahead, so it is never overwritten while still being read.
+__device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long long e, float *vec) {
+    const int K = A.K;
+    P2PBuf *own = reinterpret_cast<P2PBuf *>(A.peers[A.rank]);
+    const int slot = (int)(e % 3ull);
+    if (blockIdx.x == 0) {
+        for (int p = 0; p < A.ws; ++p) {
+            float *dst = reinterpret_cast<P2PBuf *>(A.peers[p])->slot[slot][A.rank];
+            for (int i = threadIdx.x; i < K; i += SKR_THREADS) dst[i] = vec[i];
+        }
+        __syncthreads();                       // bar.sync + the release below (system scope) cover every thread's stores
+        if ((int)threadIdx.x < A.ws) {
+            unsigned long long *f = &reinterpret_cast<P2PBuf *>(A.peers[threadIdx.x])->flag[A.rank];
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e + 1ull) : "memory");
+        }
+    }
+    if ((int)threadIdx.x < A.ws) {
+        const unsigned long long *f = &own->flag[threadIdx.x];
+        unsigned long long v;
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (++spins > (1u << 26)) { printf("timet: sinkhorn peer exchange timed out (rank %d waiting for rank %d, exchange %llu)\n", A.rank, (int)threadIdx.x, e); __trap(); }
+        } while (v < e + 1ull);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
+        float t = 0.f;
+        for (int r = 0; r < A.ws; ++r) t += __ldcv(&own->slot[slot][r][i]);
+        vec[i] = t;
+    }
+    __syncthreads();
 }
 
 template <int NV4>
@@ -333,7 +375,11 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
         A.partials[(size_t)blockIdx.x * K + i] = t;
     }
     grid_barrier(A.bar, (++epoch) * gridDim.x);
-    fold_partials<SKR_THREADS>(A.partials, gridDim.x, K, red, a_s, A.r);
+    fold_partials<SKR_THREADS>(A.partials, gridDim.x, K, red, a_s, 0.f);      // a_s = local column sums
+    unsigned long long xch = A.epoch0;
+    if (A.ws > 1) skr_exchange(A, xch++, a_s);
+    for (int i = threadIdx.x; i < K; i += SKR_THREADS) a_s[i] = __fdiv_rn(A.r, a_s[i]);
+    __syncthreads();
 
     for (int it = 0; it < A.iters; ++it) {
         float4 av[NV4];
@@ -385,10 +431,12 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
             atomicAdd(ufix + i, (unsigned long long)__float2ll_rn(t * 4611686018427387904.0f));
         }
         grid_barrier(A.bar, (++epoch) * gridDim.x);
-        for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
-            const float u = (float)((double)(long long)__ldcg(ufix + i) * 2.168404344971009e-19);   // * 2^-62
-            a_s[i] = a_s[i] * __fdiv_rn(A.r, u);                       // Q *= r / u  (my_utils.py:268)
-        }
+        for (int i = threadIdx.x; i < K; i += SKR_THREADS)
+            red[i] = (float)((double)(long long)__ldcg(ufix + i) * 2.168404344971009e-19);      // local u_i (* 2^-62)
+        __syncthreads();
+        if (A.ws > 1) skr_exchange(A, xch++, red);                     // u_i summed over ranks (my_utils.py:270-272)
+        for (int i = threadIdx.x; i < K; i += SKR_THREADS)
+            a_s[i] = a_s[i] * __fdiv_rn(A.r, red[i]);                  // Q *= r / u  (my_utils.py:268)
         if (blockIdx.x == 0) {                                         // recycle the buffer of iteration it-1 for it+2
             unsigned long long *z = A.ufix + (size_t)((it + 2) % 3) * K;
             for (int i = threadIdx.x; i < K; i += SKR_THREADS) z[i] = 0ull;
@@ -484,7 +532,11 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
         int rgrid, rpc;
         size_t rsmem;
         const char *force = getenv("TIMET_SK_STREAMING");
-        if (world_size == 1 && iters >= 1 && !(force && force[0] == '1') && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+        void **peers = nullptr;
+        int prank = 0, pws = 1;
+        unsigned long long *pepoch = nullptr;
+        const bool p2p = world_size > 1 && comm_p2p_info(comm, &peers, &prank, &pws, &pepoch) && pws == world_size && K <= P2P_MAX_K;
+        if ((world_size == 1 || p2p) && iters >= 1 && !(force && force[0] == '1') && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
             (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160) {
             float *partials = (float *)workspace;
             unsigned int *bar = (unsigned int *)(partials + (size_t)322 * K);
@@ -498,6 +550,9 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
             R.rows_per_cta = rpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
             R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
             R.r = 1.0f / (float)K; R.c = 1.0f / ((float)B * (float)world_size);
+            R.peers = p2p ? peers : nullptr; R.rank = prank; R.ws = p2p ? pws : 1;
+            R.epoch0 = p2p ? *pepoch : 0ull;
+            if (p2p) *pepoch += (unsigned long long)iters;             // pass 0 + (iters - 1) iterations exchange a vector
             switch ((K / 4 + 31) / 32) {
                 case 1: return sk_resident_launch<1>(R, rgrid, rsmem, st);
                 case 2: return sk_resident_launch<2>(R, rgrid, rsmem, st);

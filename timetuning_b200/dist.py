@@ -30,7 +30,7 @@ def broadcast_bytes(payload, nbytes: int, src: int = 0, device="cpu") -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def init_comm():
+def init_comm(p2p: bool = True):
     """Create the library communicator for the current default process group (no-op for 1 rank)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return None
@@ -48,6 +48,16 @@ def init_comm():
     handle = C.c_void_p()
     _cabi.check(lib.timet_comm_init(uid, rank, ws, C.byref(handle)), "comm_init")
     ops._comm.update(handle=handle, world_size=ws, rank=rank)
+    if p2p and dist.get_backend() == "nccl":
+        # NVLink peer-memory exchange for the resident Sinkhorn kernel: all-gather the 64-byte CUDA IPC handles
+        raw = C.create_string_buffer(_cabi.IPC_HANDLE_BYTES)
+        _cabi.check(lib.timet_comm_p2p_handle(handle, raw), "comm_p2p_handle")
+        mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).to(dev)
+        allh = [torch.empty_like(mine) for _ in range(ws)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh)
+        _cabi.check(lib.timet_comm_p2p_connect(handle, blob), "comm_p2p_connect")
+        dist.barrier()
     return handle
 
 
