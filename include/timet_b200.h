@@ -179,6 +179,7 @@ int timet_comm_destroy(timet_comm_t comm);
 #define TIMET_IPC_HANDLE_BYTES 64
 int timet_comm_p2p_handle(timet_comm_t comm, void *handle_out);
 int timet_comm_p2p_connect(timet_comm_t comm, const void *all_handles /* world_size x 64 bytes, rank order */);
+int timet_comm_p2p_disable(timet_comm_t comm); /* back to the NCCL path (all ranks must agree) */
 /* sum-all-reduce of n float32 in place on `stream` (exposed for tests of the plumbing) */
 int timet_comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, timet_stream_t stream);
 

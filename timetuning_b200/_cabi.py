@@ -49,6 +49,7 @@ _PROTOS = {
     "timet_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "timet_comm_p2p_handle": (C.c_int, [_P, _P]),
     "timet_comm_p2p_connect": (C.c_int, [_P, _P]),
+    "timet_comm_p2p_disable": (C.c_int, [_P]),
     "timet_comm_destroy": (C.c_int, [_P]),
     "timet_comm_allreduce_f32": (C.c_int, [_P, _P, C.c_int64, _P]),
 }

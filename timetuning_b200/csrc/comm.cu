@@ -153,6 +153,12 @@ int timet_comm_p2p_connect(timet_comm_t comm, const void *all_handles) {
     return TIMET_OK;
 }
 
+int timet_comm_p2p_disable(timet_comm_t comm) {
+    TIMET_CHECK_ARG(comm != nullptr, "comm_p2p_disable: NULL communicator");
+    ((Comm *)comm)->p2p_ready = false;          // Sinkhorn falls back to the NCCL all-reduce path
+    return TIMET_OK;
+}
+
 int timet_comm_destroy(timet_comm_t comm) {
     if (!comm) return TIMET_OK;
     NcclApi *api = nccl();

@@ -307,7 +307,7 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 constexpr int FIN_WARPS = 8;
 constexpr int FIN_QPB = 64;                    // consecutive queries per CTA
 
-__global__ void __launch_bounds__(FIN_WARPS * 32)
+__global__ void __launch_bounds__(FIN_WARPS * 32, 4)
 ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float *__restrict__ fn32,
                    const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_meta,
                    float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
@@ -351,16 +351,51 @@ ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float
             key = f * N + j;
             krow = (int32_t)(clip_row0 + key);
         }
-        // warp-cooperative canonical dot per candidate (coalesced 512-byte segments of the key row)
+        // warp-cooperative canonical dot, four candidates at a time: all key-row loads of a chunk are in flight
+        // together (the per-candidate chains keep their i = lane, lane+32, ... order, so the bits do not change)
         float my_sim = 0.f;
-        for (int c = 0; c < nc; ++c) {
-            const int32_t row = __shfl_sync(0xffffffffu, krow, c);
-            const float sim = dot_canonical_warp(qs, reinterpret_cast<const float4 *>(fn32 + (int64_t)row * Dp), Dp >> 2, lane);
-            if (lane == c) my_sim = sim;
+        const int n4 = Dp >> 2;
+        for (int c0 = 0; c0 < nc; c0 += 4) {
+            const float4 *kp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int32_t row = __shfl_sync(0xffffffffu, krow, (c0 + u < nc) ? c0 + u : c0);
+                kp[u] = reinterpret_cast<const float4 *>(fn32 + (int64_t)row * Dp);
+            }
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = lane; i < n4; i += 32) {
+                const float4 x = qs[i];
+                float4 y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) y[u] = __ldg(kp[u] + i);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc[u] = fma4_chain(acc[u], x, y[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float sdot = warp_sum(acc[u]);
+                if (lane == c0 + u) my_sim = sdot;
+            }
+        }
+        // canonical order (affinity desc, key asc) by counting: rank_j = #candidates that precede candidate j
+        const float my_aff = has ? affinity_from_sim(my_sim, p.temperature) : -1.f;
+        const int32_t my_key = has ? key : 0x7fffffff;
+        int rank = 0;
+        for (int i = 0; i < nc; ++i) {
+            const float a = __shfl_sync(0xffffffffu, my_aff, i);
+            const int32_t kk = __shfl_sync(0xffffffffu, my_key, i);
+            rank += (a > my_aff || (a == my_aff && kk < my_key)) ? 1 : 0;
         }
         TopList L;
         list_init(L);
-        list_offer(L, has, has ? affinity_from_sim(my_sim, p.temperature) : 0.f, key, p.topk, lane);
+        for (int i = 0; i < nc; ++i) {                 // lane r picks the candidate of rank r
+            const float a = __shfl_sync(0xffffffffu, my_aff, i);
+            const int32_t kk = __shfl_sync(0xffffffffu, my_key, i);
+            const int r = __shfl_sync(0xffffffffu, rank, i);
+            if (r == lane) { L.v = a; L.key = kk; }
+        }
+        L.cnt = nc;
+        if (nc >= p.topk) L.kth = __shfl_sync(0xffffffffu, L.v, p.topk - 1);
         const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);
         st_sel += (unsigned long long)(m < kw ? m : kw);
         st_ties += (m > p.topk);

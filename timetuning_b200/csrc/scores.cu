@@ -106,21 +106,25 @@ scores_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else {
         // epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (rows m0 + lane index), 32 columns at a time
         const int q = warp & 3;
-        const int64_t row = (int64_t)m0 + q * 32 + lane;
         if (lane == 0) ptx::mbar_wait(&ctl->tmem_full, 0);
         __syncwarp();
         ptx::tc_fence_after();
         const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16);
+        // TMEM -> registers -> a 32 x 33 shared-memory tile per warp -> coalesced 128-byte row segments
+        float *tile = reinterpret_cast<float *>(ctl + 1) + (size_t)q * 32 * 33;
         for (int c0 = 0; c0 < Np; c0 += 32) {
             uint32_t r[32];
             ptx::tmem_ld_32x32(t_acc + (uint32_t)c0, r);
             ptx::tmem_ld_wait();
-            if (row < rows) {
-                float *dst = out + row * K + n0 + c0;
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (n0 + c0 + e < K) dst[e] = __uint_as_float(r[e]);
+            for (int e = 0; e < 32; ++e) tile[lane * 33 + e] = __uint_as_float(r[e]);      // row = lane (conflict-free: stride 33)
+            __syncwarp();
+            const int col = n0 + c0 + lane;
+            for (int rr = 0; rr < 32; ++rr) {
+                const int64_t grow = (int64_t)m0 + q * 32 + rr;
+                if (grow < rows && col < K) out[grow * K + col] = tile[rr * 33 + lane];
             }
+            __syncwarp();
         }
     }
     ptx::tc_fence_before();
@@ -180,7 +184,7 @@ int timet_cosine_scores(const float *x, const float *prototypes, int64_t B, int 
         if ((rc = tc_make_map(&map_a, a2, B + 128, 2 * dhp, 128)) != TIMET_OK) return rc;
         if ((rc = tc_make_map(&map_b, b2, Kp, 2 * dhp, Np)) != TIMET_OK) return rc;
     }
-    const size_t smem = 1024 + (size_t)SC_STAGES * (128 * 128 + (size_t)Np * 128) + sizeof(ScCtl) + 64;
+    const size_t smem = 1024 + (size_t)SC_STAGES * (128 * 128 + (size_t)Np * 128) + sizeof(ScCtl) + 4 * 32 * 33 * sizeof(float) + 64;
     TIMET_CUDA(cudaFuncSetAttribute(scores_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B + 127) / 128), (unsigned)n_tiles);
     scores_gemm_kernel<<<grid, SC_THREADS, smem, st>>>(map_a, map_b, scores_out, B, K, Np, dhp);

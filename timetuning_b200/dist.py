@@ -5,6 +5,7 @@ from rank 0 to the other ranks."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -48,16 +49,30 @@ def init_comm(p2p: bool = True):
     handle = C.c_void_p()
     _cabi.check(lib.timet_comm_init(uid, rank, ws, C.byref(handle)), "comm_init")
     ops._comm.update(handle=handle, world_size=ws, rank=rank)
-    if p2p and dist.get_backend() == "nccl":
-        # NVLink peer-memory exchange for the resident Sinkhorn kernel: all-gather the 64-byte CUDA IPC handles
-        raw = C.create_string_buffer(_cabi.IPC_HANDLE_BYTES)
-        _cabi.check(lib.timet_comm_p2p_handle(handle, raw), "comm_p2p_handle")
-        mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).to(dev)
+    if p2p and dist.get_backend() == "nccl" and os.environ.get("TIMET_SK_P2P", "1") != "0":
+        # NVLink peer-memory exchange for the resident Sinkhorn kernel: all-gather the 64-byte CUDA IPC handles.
+        # Every rank must end up on the same path, so success is agreed with a MIN all-reduce.
+        ok = 1
+        blob = b""
+        try:
+            raw = C.create_string_buffer(_cabi.IPC_HANDLE_BYTES)
+            _cabi.check(lib.timet_comm_p2p_handle(handle, raw), "comm_p2p_handle")
+            mine = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).to(dev)
+        except RuntimeError:
+            ok, mine = 0, torch.zeros(_cabi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
         allh = [torch.empty_like(mine) for _ in range(ws)]
         dist.all_gather(allh, mine)
-        blob = b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh)
-        _cabi.check(lib.timet_comm_p2p_connect(handle, blob), "comm_p2p_connect")
-        dist.barrier()
+        if ok:
+            try:
+                blob = b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh)
+                _cabi.check(lib.timet_comm_p2p_connect(handle, blob), "comm_p2p_connect")
+            except RuntimeError:
+                ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            _cabi.check(lib.timet_comm_p2p_disable(handle), "comm_p2p_disable")
+        ops._comm["p2p"] = bool(int(flag.item()))
     return handle
 
 
