@@ -187,11 +187,12 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         float thr = (G.flags & 2) ? INFINITY : -INFINITY;
         int cnt = 0, lost = 0;
 
-        for (int tile = buf; tile < ntiles; tile += G.nbuf) {
-            const int ci = tile / nchunks, ch = tile - ci * nchunks;
+        int ci = 0, ch = buf;                                       // tile = ci * nchunks + ch, advanced without divisions
+        while (ch >= nchunks) { ch -= nchunks; ++ci; }
+        uint32_t use = 0;
+        for (int tile = buf; tile < ntiles; tile += G.nbuf, ++use) {
             const int kr_start = kr_lo + ch * G.RPC;
             const int rc = min(G.RPC, kr_hi + 1 - kr_start);
-            const uint32_t use = (uint32_t)(tile / G.nbuf);
             if (lane == 0) ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u);   // one poller per warp: the tensor core needs the smem bandwidth
             __syncwarp();
             ptx::tc_fence_after();
@@ -245,6 +246,8 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+            ch += G.nbuf;
+            while (ch >= nchunks) { ch -= nchunks; ++ci; }
         }
 
         if (warp == 4 && lane == 0) stamp(4);
