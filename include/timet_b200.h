@@ -164,6 +164,13 @@ int timet_restrict_neighborhood(int h, int w, int radius, float *mask_out, timet
 int timet_norm_mask(const void *mask, void *out, int n_channels, int64_t hw, int dtype_bytes,
                     timet_stream_t stream);
 
+/* Eval tail of the DAVIS/YTVOS propagation (mask_propagation.py:822-824):
+ * F.interpolate(maps, size=(out_h, out_w), mode="bilinear", align_corners=False) followed by max over channels,
+ * fused.  labels: channel-last float32 frames [n_frames][h*w, C] with `frame_stride` floats between frames (the
+ * layout timet_ff_propagate writes); out: int64 [n_frames, out_h, out_w]. */
+int timet_upsample_argmax(const float *labels, int n_frames, int h, int w, int n_channels, int out_h, int out_w,
+                          int64_t frame_stride, int64_t *out, timet_stream_t stream);
+
 /* ------------------------------------------------------------------ multi-GPU plumbing
  * One process per GPU (time_tuning.py:516-521,717).  Rank 0 calls timet_comm_unique_id and
  * broadcasts the 128 bytes with whatever it has (torch.distributed in timetuning_b200/dist.py);

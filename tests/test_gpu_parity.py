@@ -307,3 +307,50 @@ def test_cosine_scores(B, K, dh):
     assert err < 2e-6, f"max abs err {err:.3e}"
     ref32 = (torch.nn.functional.normalize(cu(x), dim=-1) @ cu(p).t()).cpu().numpy()
     assert np.abs(got - ref32).max() < 2e-6
+
+
+def test_eval_tail_upsample_argmax(golden):
+    """mask_propagation.py:822-824 (bilinear align_corners=False + max over channels), fused, vs torch on the
+    reference-made propagate_eval_onehot maps; and the one-call eval pattern."""
+    g = golden("propagate_eval_onehot")
+    maps = torch.from_numpy(g["segs"])                                  # [fs-1, C, sr, sr] float64 (reference output)
+    R = g["annotation"].shape[-1]
+    up = torch.nn.functional.interpolate(maps, size=(R, R), mode="bilinear", align_corners=False)
+    want = up.max(dim=1)[1]
+    got = tb.upsample_argmax(maps.cuda(), R).cpu()
+    srt = up.sort(dim=1)[0]
+    decided = (srt[:, -1] - srt[:, -2]) > 1e-5                           # near-ties of the interpolated maps are exempt
+    assert got.shape == want.shape and got.dtype == torch.int64
+    assert (got == want)[decided].all() and decided.float().mean() > 0.95
+    first = torch.from_numpy(O.to_one_hot(g["annotation"], int(g["n_obj"]) + 1)).unsqueeze(0)
+    pred = tb.propagate_labels_eval(int(g["n_last"]), int(g["s"]), int(g["topk"]), cu(g["feats"]), first, R).cpu()
+    assert (pred == want)[decided].all()
+
+
+def test_non_square_grid_through_the_c_abi():
+    """The C ABI takes grid_h != grid_w (additive; the reference is square-only, mask_propagation.py:407): both
+    engines against a dense fp64 restatement."""
+    H, W, D, C, fs, radius, topk, n_last = 10, 24, 64, 8, 4, 3, 4, 7
+    N = H * W
+    rng = np.random.default_rng(3)
+    feats = rng.standard_normal((1, fs, N, D)).astype(np.float32)
+    first = synth.soft_labels(N, C, seed=1)
+    fn = O.l2_normalize_rows(feats[0]).astype(np.float64)
+    rows, cols = np.arange(N) // W, np.arange(N) % W
+    win = (np.abs(rows[:, None] - rows[None]) <= radius) & (np.abs(cols[:, None] - cols[None]) <= radius)
+    segs = [first.astype(np.float64)]
+    for t in range(1, fs):
+        ctx = O.context_frames(t, n_last)
+        aff = np.concatenate([np.exp(fn[t] @ fn[c].T / 0.1) * win for c in ctx], axis=1)
+        kth = np.sort(aff, axis=1)[:, -topk]
+        wgt = np.where(aff >= kth[:, None], aff, 0)
+        wgt /= wgt.sum(1, keepdims=True)
+        segs.append(wgt @ np.concatenate([segs[c] for c in ctx], axis=0))
+    for engine in ENGINES:
+        plan = tb.FFPlan(1, fs, H, W, D, C, n_last, radius, topk)
+        labels = torch.empty((1, fs, N, C), dtype=torch.float32, device="cuda")
+        labels[0, 0] = cu(first)
+        plan.propagate(cu(feats), labels, None, engine)
+        got = labels[0].cpu().numpy()
+        for t in range(1, fs):
+            assert np.abs(got[t] - segs[t]).max() < 1e-5, (engine, t)

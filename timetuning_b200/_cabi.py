@@ -45,6 +45,7 @@ _PROTOS = {
     "timet_debug_tc_trace": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, _P, C.c_int, _P]),
     "timet_restrict_neighborhood": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
     "timet_norm_mask": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P]),
+    "timet_upsample_argmax": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P]),
     "timet_comm_unique_id": (C.c_int, [_P]),
     "timet_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "timet_comm_p2p_handle": (C.c_int, [_P, _P]),

@@ -152,6 +152,45 @@ def norm_mask(mask: torch.Tensor) -> torch.Tensor:
     return out if dev_in.type == "cuda" else out.to(dev_in)
 
 
+@torch.no_grad()
+def upsample_argmax(maps: torch.Tensor, size) -> torch.Tensor:
+    """Eval tail of mask_propagation.py:822-824, fused: bilinear up-sampling (align_corners=False) of
+    maps [T, C, h, w] to `size` and arg max over channels -> int64 [T, size_h, size_w]."""
+    out_h, out_w = (size, size) if isinstance(size, int) else size
+    T, Cc, h, w = maps.shape
+    dev_in = maps.device
+    cl = _to_cuda(maps.detach()).float().permute(0, 2, 3, 1).contiguous()          # channel-last frames
+    return _upsample_argmax_cl(cl.view(T, h * w, Cc), h, w, out_h, out_w, dev_in)
+
+
+def _upsample_argmax_cl(frames_cl, h, w, out_h, out_w, dev_out=None):
+    """frames_cl: float32 [T, h*w, C] (last two dims contiguous; frames may be strided)."""
+    T, N, Cc = frames_cl.shape
+    assert N == h * w and frames_cl.stride(2) == 1 and frames_cl.stride(1) == Cc
+    out = torch.empty((T, out_h, out_w), dtype=torch.int64, device=frames_cl.device)
+    with torch.cuda.device(frames_cl.device):
+        check(_cabi.lib().timet_upsample_argmax(_ptr(frames_cl), T, h, w, Cc, out_h, out_w, frames_cl.stride(0), _ptr(out),
+                                                _stream()), "upsample_argmax")
+    return out if dev_out is None or dev_out.type == "cuda" else out.to(dev_out)
+
+
+@torch.no_grad()
+def propagate_labels_eval(n_last_frames, size_mask_neighborhood, topk, feats, first_seg, input_resolution):
+    """The whole eval call pattern of mask_propagation.py:821-824 for one video on the device: feats [fs, N, D]
+    backbone features, first_seg [1, C, H, W] (one-hot annotation of frame 0) -> int64 [fs-1, R, R] hard predictions
+    (labels stay channel-last float32 on the GPU; no float64 maps, no [T, C, R, R] tensor)."""
+    feats = _to_cuda(feats.detach()).float().contiguous()
+    fs, N, D = feats.shape
+    sr = int(round(N ** 0.5))
+    seg = torch.nn.functional.interpolate(_to_cuda(first_seg.detach()).to(torch.float64), size=(sr, sr), mode="nearest")
+    Cc = seg.shape[1]
+    first = seg[0].reshape(Cc, N).t().float()
+    labels, _ = propagate_labels_batched(feats.unsqueeze(0), first.unsqueeze(0), n_last_frames, size_mask_neighborhood,
+                                         topk, want_hard=False)
+    R = int(input_resolution)
+    return _upsample_argmax_cl(labels[0, 1:], sr, sr, R, R)
+
+
 # --------------------------------------------------------------------------- Feature-Forwarding
 class FFPlan:
     """Shapes + workspace of one Feature-Forwarding problem batch (all clips share a shape)."""
