@@ -354,3 +354,32 @@ def test_non_square_grid_through_the_c_abi():
         got = labels[0].cpu().numpy()
         for t in range(1, fs):
             assert np.abs(got[t] - segs[t]).max() < 1e-5, (engine, t)
+
+
+def test_sinkhorn_streaming_path_matches_resident(monkeypatch):
+    """The multi-launch streaming kernels (multi-GPU NCCL fallback / shapes that do not fit shared memory) against
+    the resident cooperative kernel and the oracle."""
+    scores = synth.cosine_scores(4 * 784, 200, seed=91)
+    q_res = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
+    monkeypatch.setenv("TIMET_SK_STREAMING", "1")
+    q_str = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
+    q_str2 = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
+    monkeypatch.delenv("TIMET_SK_STREAMING")
+    assert torch.equal(q_str, q_str2), "streaming path must be bit-reproducible"
+    ref = O.sinkhorn_scaling(scores, 0.05, 10, dtype=np.float64)
+    assert_close(q_str.cpu().numpy(), ref, what="streaming vs fp64 oracle")
+    assert_close(q_res.cpu().numpy(), q_str.cpu().numpy(), what="resident vs streaming", atol=1e-6, rtol=1e-5)
+
+
+def test_sinkhorn_rows_beyond_shared_memory():
+    """configs[2] at 2 GPUs has 100 352 rows per rank: more than fits in shared memory -> streaming kernels."""
+    B, K = 128 * 784, 200
+    scores = synth.cosine_scores(B, K, seed=92)
+    q = tb.sinkhorn_from_scores(cu(scores), 0.05, 10).double().cpu().numpy()
+    assert np.abs(q.sum(1) - 1).max() < 1e-5
+    col = q.sum(0) * K / B
+    assert abs(col.mean() - 1) < 1e-3
+    ref = O.sinkhorn_scaling(scores[:2048], 0.05, 0, dtype=np.float64)        # iters=0 rows are independent: sanity only
+    assert ref.shape == (2048, K)
+    full = O.sinkhorn_scaling(scores, 0.05, 10, dtype=np.float64)
+    assert_close(q, full, what="B=100352 vs fp64 oracle")
