@@ -170,10 +170,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import ctypes as C
     from timetuning_b200 import _cabi, dist as tdist, ops
-    from timetuning_b200.step import ff_sinkhorn_step
-    import torch.nn.functional as F
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
@@ -343,9 +340,11 @@ def main():
                    "sample": "best of 3 after 1 warm-up; " + CPU_SAMPLE.format(n=args.cpu_clips, thr=thr)}
         line = {"metric": "FF+Sinkhorn clips/s", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 (selection nominated in fp16 on tensor cores, re-evaluated in f32)"
-                if engine_used == "tcgen05" else "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "clips_per_gpu": bs, "global_clips": bs * world, "engine": engine_used,
+                           "precision": "all results f32; the tcgen05 kernel nominates top-k candidates from fp16 inputs / fp32 "
+                                        "accumulation and every nominated key is re-evaluated in f32 (bit-identical to the f32 engine)"
+                           if engine_used == "tcgen05" else "f32",
                            "l2": "inputs larger than L2 (backbone features %.0f MB per step)" % (d_bb.numel() * 4 / 1e6),
                            "parallelism": f"clips sharded over {world} GPU(s); Sinkhorn marginals all-reduced (NCCL)"
                            if world > 1 else "single GPU"},
