@@ -516,6 +516,7 @@ int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, c
                         const unsigned int *qcount, int64_t max_items, cudaStream_t st);
 
 int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
+int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
 
 // optional CUDA events recorded on the stream right before / after the nomination (tensor-core) kernel, so a
 // caller can time the dominant kernel alone (bench.py roofline); set through timet_ff_select_timed
@@ -535,6 +536,17 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
     const char *pe = getenv("TIMET_TC_PAIR");
     rc = (pe && pe[0] == '1') ? ff_select_tc_pair_launch(p, L, ws, st) : TIMET_ERR_UNSUPPORTED;   // opt-in
     if (rc != TIMET_OK && rc != TIMET_ERR_UNSUPPORTED) return rc;
+    if (rc == TIMET_ERR_UNSUPPORTED) {
+        // persistent kernel (ff_tc3.cu): one CTA per SM walks the work items; TIMET_TC_PERSIST=0 selects the per-tile kernel
+        const char *ps = getenv("TIMET_TC_PERSIST");
+        const char *trc = getenv("TIMET_TC_TRACE");
+        const char *flg = getenv("TIMET_TC_FLAGS");
+        const bool debug = (trc && trc[0] == '1') || (flg && atoi(flg) != 0);
+        if (!(ps && ps[0] == '0') && !debug) {
+            rc = ff_select_tc_persist_launch(p, L, ws, st);
+            if (rc != TIMET_OK && rc != TIMET_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if (rc == TIMET_ERR_UNSUPPORTED) {
         const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
         CUtensorMap map_a, map_b;

@@ -1,0 +1,326 @@
+// FF stage 2, TC engine, PERSISTENT variant of the 1-CTA kernel in ff_tc.cu (same maths, same candidate format).
+//
+// Why: with one CTA per (clip, target frame, query tile) about 10 us of every ~50 us CTA are not spent on MMAs:
+// barrier/TMEM set-up, the load of the query tile, the drain of the last key tiles through the epilogue, the merge
+// of the candidate lists and the publish (profiles/tc_trace.py); shared memory allows only one CTA per SM, so nothing
+// overlaps them.  Here one CTA per SM walks a static round-robin sequence of work items and the three roles run
+// decoupled: while the epilogue groups drain / merge / publish item i, the producer already loads the query tile of
+// item i+1 (as soon as the last MMA of item i has retired: a_free barrier) and the MMA warp fills the TMEM buffers
+// with its first key tiles.  TMEM buffer and smem ring phases simply continue across items.
+//
+// Hazards handled explicitly:
+//   * query tile A is single-buffered        -> a_free mbarrier, committed after the last MMA of the item
+//   * per-query shared threshold             -> two copies, alternating per item; group 1 resets the idle copy
+//   * candidate lists of groups 1-3          -> they PUSH their entries into list 0 between two named barriers
+//                                               (group 0 never reads another group's list while that group has
+//                                               moved on to the next item)
+#include <stdlib.h>
+
+#include "ff_tc_dev.cuh"
+
+namespace timet {
+
+struct __align__(8) PsCtl {
+    uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], a_full, a_free, tmem_full[4], tmem_empty[4];
+    uint64_t item_bar[4];      // item_id[k & 3] is valid (dynamic work distribution: the producer fetches, everyone follows)
+    int32_t item_id[4];
+    uint32_t tmem_base;
+    uint32_t thr_sh[2][128];
+    uint32_t xchg[TC_GROUPS][128];
+};
+
+struct Item {
+    int t, clip, qr0, nq, kr_lo, kr_hi, nchunks, nctx, ntiles, q_row0;
+    int64_t clip_row0;
+};
+
+__device__ __forceinline__ Item item_geom(const TcGeom &G, int64_t id) {
+    Item I;
+    const int per_clip = G.nT * G.tiles_per_frame;
+    const int grp = (int)(id / ((int64_t)G.clip_group * per_clip));
+    const int grp_clips = min(G.clip_group, G.n_clips - grp * G.clip_group);
+    const int in_grp = (int)(id - (int64_t)grp * G.clip_group * per_clip);
+    const int per_t = grp_clips * G.tiles_per_frame;
+    const int tdesc = in_grp / per_t;
+    const int rem = in_grp - tdesc * per_t;
+    I.t = G.n_frames - 1 - tdesc;
+    I.clip = grp * G.clip_group + rem / G.tiles_per_frame;
+    const int qt = rem % G.tiles_per_frame;
+    I.qr0 = qt * G.QR;
+    const int qr1 = min(G.H - 1, I.qr0 + G.QR - 1);
+    I.nq = (qr1 - I.qr0 + 1) * G.W;
+    I.kr_lo = max(0, I.qr0 - G.radius);
+    I.kr_hi = min(G.H - 1, qr1 + G.radius);
+    I.nchunks = (I.kr_hi - I.kr_lo + G.RPC) / G.RPC;
+    I.nctx = ctx_count(I.t, G.n_last);
+    I.ntiles = I.nctx * I.nchunks;
+    I.clip_row0 = (int64_t)I.clip * G.n_frames * G.N;
+    I.q_row0 = (int)(I.clip_row0 + (int64_t)I.t * G.N + I.qr0 * G.W);
+    return I;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom G,
+                     uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, unsigned int *__restrict__ next_item) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    const uint32_t b_stage_bytes = (uint32_t)G.NT * 128u;
+    uint8_t *sB = sA + (size_t)G.NKC * 16384;
+    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * b_stage_bytes);
+    PsCtl *ctl = reinterpret_cast<PsCtl *>(sList + TC_GROUPS * TC_CAP * 128);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = G.total_tiles;          // work items = query tiles
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < G.nstages; ++s) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
+        ptx::mbar_init(&ctl->a_full, 1);
+        ptx::mbar_init(&ctl->a_free, 1);
+        for (int i = 0; i < 4; ++i) ptx::mbar_init(&ctl->item_bar[i], 1);
+        for (int b = 0; b < G.nbuf; ++b) { ptx::mbar_init(&ctl->tmem_full[b], 1); ptx::mbar_init(&ctl->tmem_empty[b], G.nbuf == 4 ? 4 : 8); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<512>(&ctl->tmem_base);
+    if (warp == 3) for (int i = lane; i < 256; i += 32) (&ctl->thr_sh[0][0])[i] = thr_enc(-INFINITY);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t k = 0;; ++k) {
+                // dynamic work distribution: items are handed out in heavy-first order by a global counter; the id is
+                // broadcast to the MMA warp and the epilogue groups through a 4-entry ring (the producer is never
+                // more than 2 items ahead of the slowest role, see a_free / tmem_empty)
+                const unsigned int raw = atomicAdd(next_item, 1u);
+                const int64_t id = (int64_t)raw;
+                ctl->item_id[k & 3u] = (id < total) ? (int32_t)id : -1;
+                ptx::mbar_arrive(&ctl->item_bar[k & 3u]);
+                if (id >= total) break;
+                const Item I = item_geom(G, id);
+                ptx::mbar_wait(&ctl->a_free, (k & 1u) ^ 1u);          // every MMA of the previous item has read A
+                ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
+                for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, I.q_row0, &ctl->a_full);
+                for (int ci = 0; ci < I.nctx; ++ci) {
+                    const int f = ctx_frame(I.t, G.n_last, ci);
+                    for (int ch = 0; ch < I.nchunks; ++ch) {
+                        const int k_row0 = (int)(I.clip_row0 + (int64_t)f * G.N + (I.kr_lo + ch * G.RPC) * G.W);
+                        for (int kc = 0; kc < G.NKC; ++kc) {
+                            ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
+                            ptx::mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
+                            ptx::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, kc * 64, k_row0, &ctl->full[stage]);
+                            if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sA)), db0 = ptx::umma_desc_sw128(ptx::smem_u32(sB));
+            const uint32_t stage_step = b_stage_bytes >> 4;
+            uint32_t stage = 0, phase = 0, buf = 0, use = 0;
+            for (uint32_t k = 0;; ++k) {
+                ptx::mbar_wait(&ctl->item_bar[k & 3u], (k >> 2) & 1u);
+                const int32_t id = ctl->item_id[k & 3u];
+                if (id < 0) break;
+                const Item I = item_geom(G, id);
+                ptx::mbar_wait(&ctl->a_full, k & 1u);
+                ptx::tc_fence_after();
+                int ch = 0;
+                for (int tile = 0; tile < I.ntiles; ++tile) {
+                    const int rc = min(G.RPC, I.kr_hi + 1 - (I.kr_lo + ch * G.RPC));
+                    const int n_mma = min(G.NT, (rc + G.qrows - 1) / G.qrows * G.qrows * G.W);
+                    const uint32_t idesc = ptx::umma_idesc_f16(128, n_mma);
+                    ptx::mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)G.buf_cols;
+                    uint64_t da = da0;
+                    for (int kc = 0; kc < G.NKC; ++kc, da += 16384 >> 4) {
+                        ptx::mbar_wait(&ctl->full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint64_t db = db0 + (uint64_t)(stage * stage_step);
+                        ptx::umma_f16(d_tmem, da, db, idesc, kc != 0);
+                        ptx::umma_f16(d_tmem, da + 2, db + 2, idesc, true);
+                        ptx::umma_f16(d_tmem, da + 4, db + 4, idesc, true);
+                        ptx::umma_f16(d_tmem, da + 6, db + 6, idesc, true);
+                        ptx::umma_commit(&ctl->empty[stage]);
+                        if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
+                    }
+                    ptx::umma_commit(&ctl->tmem_full[buf]);
+                    if (++buf == (uint32_t)G.nbuf) { buf = 0; ++use; }
+                    if (++ch == I.nchunks) ch = 0;
+                }
+                ptx::umma_commit(&ctl->a_free);                         // A may be overwritten once these MMAs retired
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================== epilogue groups ===========================
+        const int g = (warp - 4) >> 2;
+        const int mybuf = (G.nbuf == 4) ? g : (g & 1);
+        const int row_par = (G.nbuf == 4) ? -1 : (g >> 1);
+        const int qi = ((warp & 3) << 5) + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) << 5) << 16;
+        const uint32_t list0 = ptx::smem_u32(sList + qi);
+        const uint32_t list = list0 + (uint32_t)g * TC_CAP * 128u * 4u;
+        constexpr int half = TC_CAP / 2;
+        const uint32_t t_acc = tmem_base + (uint32_t)(mybuf * G.buf_cols) + lane_base;
+        uint32_t gtile = 0;                                            // tiles issued before this item (all roles agree)
+        for (uint32_t k = 0;; ++k) {
+            if (lane == 0) ptx::mbar_wait(&ctl->item_bar[k & 3u], (k >> 2) & 1u);
+            __syncwarp();
+            const int32_t id = ctl->item_id[k & 3u];
+            if (id < 0) break;
+            const Item I = item_geom(G, id);
+            uint32_t *thr_cur = ctl->thr_sh[k & 1u];
+            const bool valid = qi < I.nq;
+            const int qrow = I.qr0 + qi / G.W, qcol = qi % G.W;
+            const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
+            const int c_lo = qcol - G.radius;
+            const int c_lo_cl = max(c_lo, 0), c_hi_cl = min(qcol + G.radius, G.W - 1);
+            float thr = -INFINITY;
+            int cnt = 0, lost = 0;
+
+            // first tile of this item that lands in my buffer: (gtile + j) % nbuf == mybuf
+            int j = (int)(((uint32_t)mybuf + (uint32_t)G.nbuf - (gtile % (uint32_t)G.nbuf)) % (uint32_t)G.nbuf);
+            int ci = 0, ch = j;
+            while (ch >= I.nchunks) { ch -= I.nchunks; ++ci; }
+            uint32_t use = (gtile + (uint32_t)j) / (uint32_t)G.nbuf;
+            for (; j < I.ntiles; j += G.nbuf, ++use) {
+                const int kr_start = I.kr_lo + ch * G.RPC;
+                const int rc = min(G.RPC, I.kr_hi + 1 - kr_start);
+                if (lane == 0) ptx::mbar_wait(&ctl->tmem_full[mybuf], use & 1u);
+                __syncwarp();
+                ptx::tc_fence_after();
+                thr = fmaxf(thr, thr_dec(thr_cur[qi]));
+                for (int rr = 0; rr < rc; ++rr) {
+                    if (row_par >= 0 && (rr & 1) != row_par) continue;
+                    const int kr = kr_start + rr;
+                    const bool row_ok = valid && kr >= r_lo && kr <= r_hi;
+                    if (!__any_sync(0xffffffffu, row_ok)) continue;
+                    const int code_row = (ci << 10) | ((kr - r_lo) << 5);
+                    for (int cb = 0; cb < G.W; cb += 16) {
+                        int col0 = rr * G.W + cb;
+                        const int shift = max(0, col0 + 16 - G.buf_cols);
+                        col0 -= shift;
+                        const int cb_eff = cb - shift;
+                        uint32_t r[16];
+                        ptx::tmem_ld_32x16(t_acc + (uint32_t)col0, r);
+                        const int lo = max(c_lo_cl - cb_eff, shift), hi = min(c_hi_cl - cb_eff, 15);
+                        uint32_t wmask = 0u;
+                        if (row_ok && hi >= lo) wmask = (0xFFFFu >> (15 - hi)) & (0xFFFFu << lo) & 0xFFFFu;
+                        const uint32_t code0 = (uint32_t)(code_row + (cb_eff - c_lo));
+                        uint32_t slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
+                        ptx::tmem_ld_wait();
+#define TC_OFFER(E) tc_offer<(1u << (E))>(slot, __uint_as_float(r[E]), thr, wmask, code0 + (E));
+                        TC_OFFER(0) TC_OFFER(1) TC_OFFER(2) TC_OFFER(3) TC_OFFER(4) TC_OFFER(5) TC_OFFER(6) TC_OFFER(7)
+                        TC_OFFER(8) TC_OFFER(9) TC_OFFER(10) TC_OFFER(11) TC_OFFER(12) TC_OFFER(13) TC_OFFER(14) TC_OFFER(15)
+#undef TC_OFFER
+                        cnt = (int)((slot - list) / TC_SLOT_STRIDE);
+                        if (__any_sync(0xffffffffu, cnt > half)) {
+                            const float before = thr;
+                            tc_compact(list, cnt, thr, lost, G.topk, half);
+                            if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[mybuf]);
+                ch += G.nbuf;
+                while (ch >= I.nchunks) { ch -= I.nchunks; ++ci; }
+            }
+            gtile += (uint32_t)I.ntiles;
+
+            // ---- final phase of the item (the MMA warp is already working on the next one)
+            {
+                const float before = thr;
+                tc_compact(list, cnt, thr, lost, G.topk, half);
+                if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));
+            }
+            if (g == 1) ctl->thr_sh[(k + 1u) & 1u][qi] = thr_enc(-INFINITY);   // idle copy, used by the next item
+            asm volatile("bar.sync 1, 512;" ::: "memory");            // (A) every group's final threshold is published
+            thr = fmaxf(thr, thr_dec(thr_cur[qi]));
+            tc_filter(list, cnt, thr);
+            ctl->xchg[g][qi] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
+            asm volatile("bar.sync 1, 512;" ::: "memory");            // (B) counts known -> push offsets
+            int off = 0, tot = 0, any_lost = 0;
+#pragma unroll
+            for (int og = 0; og < TC_GROUPS; ++og) {
+                const uint32_t x = ctl->xchg[og][qi];
+                if (og < g) off += (int)(x & 0xFFFFu);
+                tot += (int)(x & 0xFFFFu);
+                any_lost |= (int)(x >> 16);
+            }
+            if (g > 0) {
+                for (int s = 0; s < cnt; ++s)
+                    if (off + s < TC_CAP) sts_u32(list0 + (uint32_t)(off + s) * TC_SLOT_STRIDE, lds_u32(list + s * TC_SLOT_STRIDE));
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");            // (C) list 0 holds the merged candidates
+            if (g == 0) {
+                lost = any_lost | (tot > TC_CAP ? 1 : 0);
+                cnt = min(tot, TC_CAP);
+                tc_compact(list0, cnt, thr, lost, G.topk, FF_CAND_STORE);
+                if (valid) {
+                    const int64_t q = ((int64_t)I.clip * G.nT + (I.t - G.t_begin)) * G.N + I.qr0 * G.W + qi;
+                    uint32_t *dst = cand + q * FF_CAND_STORE;
+#pragma unroll
+                    for (int s4 = 0; s4 < FF_CAND_STORE; s4 += 4) {
+                        if (s4 < cnt) {
+                            uint4 v;
+                            v.x = lds_u32(list0 + (s4 + 0) * TC_SLOT_STRIDE); v.y = lds_u32(list0 + (s4 + 1) * TC_SLOT_STRIDE);
+                            v.z = lds_u32(list0 + (s4 + 2) * TC_SLOT_STRIDE); v.w = lds_u32(list0 + (s4 + 3) * TC_SLOT_STRIDE);
+                            *reinterpret_cast<uint4 *>(dst + s4) = v;
+                        }
+                    }
+                    cand_meta[q] = (uint32_t)cnt | (lost ? 0x10000u : 0u);
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+static size_t persist_smem_bytes(const TcGeom &G) {
+    return 1024 + (size_t)G.NKC * 16384 + (size_t)G.nstages * G.NT * 128 + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(PsCtl) + 64;
+}
+
+// Persistent launch; TIMET_ERR_UNSUPPORTED if the shape does not qualify (caller falls back to the per-tile kernel)
+int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
+    TcGeom G;
+    if (!tc_geometry(p, L, &G) || !G.a_resident) return TIMET_ERR_UNSUPPORTED;
+    G.nstages = TC_MAX_STAGES;
+    const char *ns = getenv("TIMET_TC_STAGES");
+    if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G.nstages = atoi(ns);
+    while (persist_smem_bytes(G) > 227 * 1024 && G.nstages > 2) G.nstages--;
+    if (persist_smem_bytes(G) > 227 * 1024) return TIMET_ERR_UNSUPPORTED;
+    const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
+    CUtensorMap map_a, map_b;
+    int rc;
+    if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+    if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
+    const size_t smem = persist_smem_bytes(G);
+    TIMET_CUDA(cudaFuncSetAttribute(ff_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = G.total_tiles < num_sms() ? G.total_tiles : num_sms();
+    unsigned int *next_item = reinterpret_cast<unsigned int *>(ws + L.off_redo + 128);   // zeroed with the redo header by timet_ff_select
+    ff_tc_persist_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(map_a, map_b, G, reinterpret_cast<uint32_t *>(ws + L.off_cand),
+                                                                  reinterpret_cast<uint32_t *>(ws + L.off_cand_meta), next_item);
+    TIMET_LAUNCHED();
+    return TIMET_OK;
+}
+
+}  // namespace timet
