@@ -66,8 +66,10 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     const uint32_t b_stage_bytes = (uint32_t)G.NT * 128u;
-    uint8_t *sB = sA + (size_t)G.NKC * 16384;
-    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * b_stage_bytes);
+    const uint32_t a_in_stage = G.a_resident ? 0u : 16384u;       // D > 384: the A chunk rides in front of every B chunk
+    const uint32_t stage_bytes = b_stage_bytes + a_in_stage;
+    uint8_t *sB = sA + (G.a_resident ? (size_t)G.NKC * 16384 : 0);
+    uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * stage_bytes);
     PsCtl *ctl = reinterpret_cast<PsCtl *>(sList + TC_GROUPS * TC_CAP * 128);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total = G.total_tiles;          // work items = query tiles
@@ -105,17 +107,21 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 ptx::mbar_arrive(&ctl->item_bar[k & 3u]);
                 if (id >= total) break;
                 const Item I = item_geom(G, id);
-                ptx::mbar_wait(&ctl->a_free, (k & 1u) ^ 1u);          // every MMA of the previous item has read A
-                ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
-                for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, I.q_row0, &ctl->a_full);
+                if (G.a_resident) {
+                    ptx::mbar_wait(&ctl->a_free, (k & 1u) ^ 1u);      // every MMA of the previous item has read A
+                    ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
+                    for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, I.q_row0, &ctl->a_full);
+                }
                 for (int ci = 0; ci < I.nctx; ++ci) {
                     const int f = ctx_frame(I.t, G.n_last, ci);
                     for (int ch = 0; ch < I.nchunks; ++ch) {
                         const int k_row0 = (int)(I.clip_row0 + (int64_t)f * G.N + (I.kr_lo + ch * G.RPC) * G.W);
                         for (int kc = 0; kc < G.NKC; ++kc) {
                             ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
-                            ptx::mbar_expect_tx(&ctl->full[stage], b_stage_bytes);
-                            ptx::tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, kc * 64, k_row0, &ctl->full[stage]);
+                            ptx::mbar_expect_tx(&ctl->full[stage], stage_bytes);
+                            uint8_t *stp = sB + (size_t)stage * stage_bytes;
+                            if (!G.a_resident) ptx::tma_load_2d(stp, &map_a, kc * 64, I.q_row0, &ctl->full[stage]);
+                            ptx::tma_load_2d(stp + a_in_stage, &map_b, kc * 64, k_row0, &ctl->full[stage]);
                             if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                         }
                     }
@@ -126,14 +132,14 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // =========================== MMA issuer ===========================
         if (lane == 0) {
             const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sA)), db0 = ptx::umma_desc_sw128(ptx::smem_u32(sB));
-            const uint32_t stage_step = b_stage_bytes >> 4;
+            const uint32_t stage_step = stage_bytes >> 4, a_step = a_in_stage >> 4;
             uint32_t stage = 0, phase = 0, buf = 0, use = 0;
             for (uint32_t k = 0;; ++k) {
                 ptx::mbar_wait(&ctl->item_bar[k & 3u], (k >> 2) & 1u);
                 const int32_t id = ctl->item_id[k & 3u];
                 if (id < 0) break;
                 const Item I = item_geom(G, id);
-                ptx::mbar_wait(&ctl->a_full, k & 1u);
+                if (G.a_resident) ptx::mbar_wait(&ctl->a_full, k & 1u);
                 ptx::tc_fence_after();
                 int ch = 0;
                 for (int tile = 0; tile < I.ntiles; ++tile) {
@@ -147,11 +153,13 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     for (int kc = 0; kc < G.NKC; ++kc, da += 16384 >> 4) {
                         ptx::mbar_wait(&ctl->full[stage], phase);
                         ptx::tc_fence_after();
-                        const uint64_t db = db0 + (uint64_t)(stage * stage_step);
-                        ptx::umma_f16(d_tmem, da, db, idesc, kc != 0);
-                        ptx::umma_f16(d_tmem, da + 2, db + 2, idesc, true);
-                        ptx::umma_f16(d_tmem, da + 4, db + 4, idesc, true);
-                        ptx::umma_f16(d_tmem, da + 6, db + 6, idesc, true);
+                        const uint64_t ds = db0 + (uint64_t)(stage * stage_step);
+                        const uint64_t db = ds + a_step;
+                        const uint64_t dq = G.a_resident ? da : ds;
+                        ptx::umma_f16(d_tmem, dq, db, idesc, kc != 0);
+                        ptx::umma_f16(d_tmem, dq + 2, db + 2, idesc, true);
+                        ptx::umma_f16(d_tmem, dq + 4, db + 4, idesc, true);
+                        ptx::umma_f16(d_tmem, dq + 6, db + 6, idesc, true);
                         ptx::umma_commit(&ctl->empty[stage]);
                         if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                     }
@@ -159,7 +167,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     if (++buf == (uint32_t)G.nbuf) { buf = 0; ++use; }
                     if (++ch == I.nchunks) ch = 0;
                 }
-                ptx::umma_commit(&ctl->a_free);                         // A may be overwritten once these MMAs retired
+                if (G.a_resident) ptx::umma_commit(&ctl->a_free);       // A may be overwritten once these MMAs retired
             }
         }
     } else if (warp >= 4) {
@@ -296,13 +304,14 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 }
 
 static size_t persist_smem_bytes(const TcGeom &G) {
-    return 1024 + (size_t)G.NKC * 16384 + (size_t)G.nstages * G.NT * 128 + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(PsCtl) + 64;
+    const size_t a_res = G.a_resident ? (size_t)G.NKC * 16384 : 0, a_stage = G.a_resident ? 0 : 16384;
+    return 1024 + a_res + (size_t)G.nstages * ((size_t)G.NT * 128 + a_stage) + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(PsCtl) + 64;
 }
 
 // Persistent launch; TIMET_ERR_UNSUPPORTED if the shape does not qualify (caller falls back to the per-tile kernel)
 int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
     TcGeom G;
-    if (!tc_geometry(p, L, &G) || !G.a_resident) return TIMET_ERR_UNSUPPORTED;
+    if (!tc_geometry(p, L, &G)) return TIMET_ERR_UNSUPPORTED;
     G.nstages = TC_MAX_STAGES;
     const char *ns = getenv("TIMET_TC_STAGES");
     if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G.nstages = atoi(ns);
