@@ -3,7 +3,7 @@
 // Why: with one CTA per (clip, target frame, query tile) about 10 us of every ~50 us CTA are not spent on MMAs:
 // barrier/TMEM set-up, the load of the query tile, the drain of the last key tiles through the epilogue, the merge
 // of the candidate lists and the publish (profiles/tc_trace.py); shared memory allows only one CTA per SM, so nothing
-// overlaps them.  Here one CTA per SM walks a static round-robin sequence of work items and the three roles run
+// overlaps them.  Here one CTA per SM walks a static sequence of work items (see item_at) and the three roles run
 // decoupled: while the epilogue groups drain / merge / publish item i, the producer already loads the query tile of
 // item i+1 (as soon as the last MMA of item i has retired: a_free barrier) and the MMA warp fills the TMEM buffers
 // with its first key tiles.  TMEM buffer and smem ring phases simply continue across items.
@@ -14,6 +14,13 @@
 //   * candidate lists of groups 1-3          -> they PUSH their entries into list 0 between two named barriers
 //                                               (group 0 never reads another group's list while that group has
 //                                               moved on to the next item)
+//
+// Issue path.  The producer and the MMA warp run their loops with ALL 32 lanes on warp-uniform values (the item sequence
+// is a function of blockIdx and kernel parameters only) and elect one lane per TMA / MMA / commit.  With a divergent
+// `if (lane == 0)` around the loops ptxas cannot keep descriptors in uniform registers and wraps every UTCHMMA / UTMALDG
+// in an ELECT + 7 x R2UR "waterfall" (about 100 scalar instructions per 64-wide K chunk, more than the 504 cycles the
+// four MMAs of the chunk take): the tensor pipe then idles on instruction issue.  Both warps also take the HIGHEST warp
+// ids, which the SMSP arbiter favours over the 16 epilogue warps.
 #include <stdlib.h>
 
 #include "ff_tc_dev.cuh"
@@ -22,7 +29,7 @@ namespace timet {
 
 struct __align__(8) PsCtl {
     uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], a_full, a_free, tmem_full[4], tmem_empty[4];
-    uint64_t item_bar[4];      // item_id[k & 3] is valid (dynamic work distribution: the producer fetches, everyone follows)
+    uint64_t item_bar[4];      // DYN: item_id[k & 3] is valid (the producer fetches from a global counter, everyone follows)
     int32_t item_id[4];
     uint32_t tmem_base;
     uint32_t thr_sh[2][128];
@@ -59,6 +66,17 @@ __device__ __forceinline__ Item item_geom(const TcGeom &G, int64_t id) {
     return I;
 }
 
+// k-th work item of this CTA, or -1.  Items are numbered heavy-first (item_geom); row k of the schedule holds ids
+// [k * grid, (k + 1) * grid) and is walked alternately left-to-right and right-to-left ("snake"), so that a CTA that got a
+// heavier item in one row gets a lighter one in the next.  Pure function of (blockIdx, k): every role derives the same
+// sequence without communication, and the values stay warp-uniform for ptxas.
+__device__ __forceinline__ int64_t item_at(uint32_t k, int64_t total) {
+    const int64_t row0 = (int64_t)k * gridDim.x;
+    const int64_t id = row0 + ((k & 1u) ? (int64_t)(gridDim.x - 1u - blockIdx.x) : (int64_t)blockIdx.x);
+    return (row0 < total && id < total) ? id : -1;
+}
+
+template <bool DYN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom G,
                      uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, unsigned int *__restrict__ next_item) {
@@ -71,14 +89,17 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     uint8_t *sB = sA + (G.a_resident ? (size_t)G.NKC * 16384 : 0);
     uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * stage_bytes);
     PsCtl *ctl = reinterpret_cast<PsCtl *>(sList + TC_GROUPS * TC_CAP * 128);
+    // roles: warps 0-15 = epilogue groups (TMEM lane quadrant = warp & 3), 16 = TMA producer, 17 = MMA issuer,
+    // 18 = TMEM allocator, 19 = threshold init
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_PROD = 16, W_MMA = 17, W_ALLOC = 18, W_INIT = 19;
     const int64_t total = G.total_tiles;          // work items = query tiles
 
-    if (warp == 0 && lane == 0) {
+    if (warp == W_PROD && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < G.nstages; ++s) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
         ptx::mbar_init(&ctl->a_full, 1);
         ptx::mbar_init(&ctl->a_free, 1);
@@ -86,93 +107,114 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int b = 0; b < G.nbuf; ++b) { ptx::mbar_init(&ctl->tmem_full[b], 1); ptx::mbar_init(&ctl->tmem_empty[b], G.nbuf == 4 ? 4 : 8); }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) ptx::tmem_alloc<512>(&ctl->tmem_base);
-    if (warp == 3) for (int i = lane; i < 256; i += 32) (&ctl->thr_sh[0][0])[i] = thr_enc(-INFINITY);
+    if (warp == W_ALLOC) ptx::tmem_alloc<512>(&ctl->tmem_base);
+    if (warp == W_INIT) for (int i = lane; i < 256; i += 32) (&ctl->thr_sh[0][0])[i] = thr_enc(-INFINITY);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = ctl->tmem_base;
+    // the CTA owns all 512 TMEM columns, so the allocation starts at column 0 / lane 0; using the literal keeps the
+    // accumulator addresses warp-uniform for ptxas
+    if (ctl->tmem_base != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
 
-    if (warp == 0) {
-        // =========================== TMA producer ===========================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (uint32_t k = 0;; ++k) {
-                // dynamic work distribution: items are handed out in heavy-first order by a global counter; the id is
-                // broadcast to the MMA warp and the epilogue groups through a 4-entry ring (the producer is never
-                // more than 2 items ahead of the slowest role, see a_free / tmem_empty)
-                const unsigned int raw = atomicAdd(next_item, 1u);
-                const int64_t id = (int64_t)raw;
-                ctl->item_id[k & 3u] = (id < total) ? (int32_t)id : -1;
-                ptx::mbar_arrive(&ctl->item_bar[k & 3u]);
-                if (id >= total) break;
-                const Item I = item_geom(G, id);
-                if (G.a_resident) {
-                    ptx::mbar_wait(&ctl->a_free, (k & 1u) ^ 1u);      // every MMA of the previous item has read A
+    if (warp == W_PROD) {
+        // =========================== TMA producer (32 lanes, one elected per issue) ===========================
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t k = 0;; ++k) {
+            int64_t id;
+            if (DYN) {
+                // dynamic work distribution: heavy-first ids from a global counter, broadcast through a 4-entry ring (the
+                // producer is never more than 2 items ahead of the slowest role, see a_free / tmem_empty)
+                unsigned int raw = 0;
+                if (lane == 0) {
+                    raw = atomicAdd(next_item, 1u);
+                    ctl->item_id[k & 3u] = ((int64_t)raw < total) ? (int32_t)raw : -1;
+                    ptx::mbar_arrive(&ctl->item_bar[k & 3u]);
+                }
+                raw = __shfl_sync(0xffffffffu, raw, 0);
+                id = ((int64_t)raw < total) ? (int64_t)raw : -1;
+            } else {
+                id = item_at(k, total);
+            }
+            if (id < 0) break;
+            const Item I = item_geom(G, id);
+            if (G.a_resident) {
+                ptx::mbar_wait(&ctl->a_free, (k & 1u) ^ 1u);          // every MMA of the previous item has read A
+                if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
                     for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, I.q_row0, &ctl->a_full);
                 }
-                for (int ci = 0; ci < I.nctx; ++ci) {
-                    const int f = ctx_frame(I.t, G.n_last, ci);
-                    for (int ch = 0; ch < I.nchunks; ++ch) {
-                        const int k_row0 = (int)(I.clip_row0 + (int64_t)f * G.N + (I.kr_lo + ch * G.RPC) * G.W);
-                        for (int kc = 0; kc < G.NKC; ++kc) {
-                            ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
+            }
+            for (int ci = 0; ci < I.nctx; ++ci) {
+                // context frames are walked NEWEST FIRST (slot nctx-1 = frame t-1 ... slot 0 = first frame): the best matches
+                // sit in the nearest frames, so the nomination threshold is close to final after the first key tiles and
+                // the later ones append (and compact) almost nothing.  flags & 8 restores oldest-first for comparison.
+                const int f = ctx_frame(I.t, G.n_last, (G.flags & 8) ? ci : I.nctx - 1 - ci);
+                for (int ch = 0; ch < I.nchunks; ++ch) {
+                    const int k_row0 = (int)(I.clip_row0 + (int64_t)f * G.N + (I.kr_lo + ch * G.RPC) * G.W);
+                    for (int kc = 0; kc < G.NKC; ++kc) {
+                        ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
+                        if (ptx::elect_one()) {
                             ptx::mbar_expect_tx(&ctl->full[stage], stage_bytes);
                             uint8_t *stp = sB + (size_t)stage * stage_bytes;
                             if (!G.a_resident) ptx::tma_load_2d(stp, &map_a, kc * 64, I.q_row0, &ctl->full[stage]);
                             ptx::tma_load_2d(stp + a_in_stage, &map_b, kc * 64, k_row0, &ctl->full[stage]);
-                            if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                         }
+                        if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sA)), db0 = ptx::umma_desc_sw128(ptx::smem_u32(sB));
-            const uint32_t stage_step = stage_bytes >> 4, a_step = a_in_stage >> 4;
-            uint32_t stage = 0, phase = 0, buf = 0, use = 0;
-            for (uint32_t k = 0;; ++k) {
+    } else if (warp == W_MMA) {
+        // =========================== MMA issuer (32 lanes, one elected per issue) ===========================
+        const uint64_t da0 = ptx::umma_desc_sw128(ptx::smem_u32(sA)), db0 = ptx::umma_desc_sw128(ptx::smem_u32(sB));
+        const uint32_t stage_step = stage_bytes >> 4, a_step = a_in_stage >> 4;
+        uint32_t stage = 0, phase = 0, buf = 0, use = 0;
+        for (uint32_t k = 0;; ++k) {
+            int64_t id;
+            if (DYN) {
                 ptx::mbar_wait(&ctl->item_bar[k & 3u], (k >> 2) & 1u);
-                const int32_t id = ctl->item_id[k & 3u];
-                if (id < 0) break;
-                const Item I = item_geom(G, id);
-                if (G.a_resident) ptx::mbar_wait(&ctl->a_full, k & 1u);
+                id = ctl->item_id[k & 3u];
+            } else {
+                id = item_at(k, total);
+            }
+            if (id < 0) break;
+            const Item I = item_geom(G, id);
+            if (G.a_resident) ptx::mbar_wait(&ctl->a_full, k & 1u);
+            ptx::tc_fence_after();
+            int ch = 0;
+            for (int tile = 0; tile < I.ntiles; ++tile) {
+                const int rc = min(G.RPC, I.kr_hi + 1 - (I.kr_lo + ch * G.RPC));
+                const int n_mma = min(G.NT, (rc + G.qrows - 1) / G.qrows * G.qrows * G.W);
+                const uint32_t idesc = ptx::umma_idesc_f16(128, n_mma);
+                ptx::mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);
                 ptx::tc_fence_after();
-                int ch = 0;
-                for (int tile = 0; tile < I.ntiles; ++tile) {
-                    const int rc = min(G.RPC, I.kr_hi + 1 - (I.kr_lo + ch * G.RPC));
-                    const int n_mma = min(G.NT, (rc + G.qrows - 1) / G.qrows * G.qrows * G.W);
-                    const uint32_t idesc = ptx::umma_idesc_f16(128, n_mma);
-                    ptx::mbar_wait(&ctl->tmem_empty[buf], (use & 1u) ^ 1u);
+                const uint32_t d_tmem = tmem_base + buf * (uint32_t)G.buf_cols;
+                uint64_t da = da0;
+                for (int kc = 0; kc < G.NKC; ++kc, da += 16384 >> 4) {
+                    ptx::mbar_wait(&ctl->full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)G.buf_cols;
-                    uint64_t da = da0;
-                    for (int kc = 0; kc < G.NKC; ++kc, da += 16384 >> 4) {
-                        ptx::mbar_wait(&ctl->full[stage], phase);
-                        ptx::tc_fence_after();
-                        const uint64_t ds = db0 + (uint64_t)(stage * stage_step);
-                        const uint64_t db = ds + a_step;
-                        const uint64_t dq = G.a_resident ? da : ds;
+                    const uint64_t ds = db0 + (uint64_t)(stage * stage_step);
+                    const uint64_t db = ds + a_step;
+                    const uint64_t dq = G.a_resident ? da : ds;
+                    if (ptx::elect_one()) {
                         ptx::umma_f16(d_tmem, dq, db, idesc, kc != 0);
                         ptx::umma_f16(d_tmem, dq + 2, db + 2, idesc, true);
                         ptx::umma_f16(d_tmem, dq + 4, db + 4, idesc, true);
                         ptx::umma_f16(d_tmem, dq + 6, db + 6, idesc, true);
                         ptx::umma_commit(&ctl->empty[stage]);
-                        if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                     }
-                    ptx::umma_commit(&ctl->tmem_full[buf]);
-                    if (++buf == (uint32_t)G.nbuf) { buf = 0; ++use; }
-                    if (++ch == I.nchunks) ch = 0;
+                    if (++stage == (uint32_t)G.nstages) { stage = 0; phase ^= 1u; }
                 }
-                if (G.a_resident) ptx::umma_commit(&ctl->a_free);       // A may be overwritten once these MMAs retired
+                if (ptx::elect_one()) ptx::umma_commit(&ctl->tmem_full[buf]);
+                if (++buf == (uint32_t)G.nbuf) { buf = 0; ++use; }
+                if (++ch == I.nchunks) ch = 0;
             }
+            if (G.a_resident && ptx::elect_one()) ptx::umma_commit(&ctl->a_free);   // A may be overwritten once these MMAs retired
         }
-    } else if (warp >= 4) {
+    } else if (warp < 16) {
         // =========================== epilogue groups ===========================
-        const int g = (warp - 4) >> 2;
+        const int g = warp >> 2;
         const int mybuf = (G.nbuf == 4) ? g : (g & 1);
         const int row_par = (G.nbuf == 4) ? -1 : (g >> 1);
         const int qi = ((warp & 3) << 5) + lane;
@@ -183,9 +225,14 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t t_acc = tmem_base + (uint32_t)(mybuf * G.buf_cols) + lane_base;
         uint32_t gtile = 0;                                            // tiles issued before this item (all roles agree)
         for (uint32_t k = 0;; ++k) {
-            if (lane == 0) ptx::mbar_wait(&ctl->item_bar[k & 3u], (k >> 2) & 1u);
-            __syncwarp();
-            const int32_t id = ctl->item_id[k & 3u];
+            int64_t id;
+            if (DYN) {
+                if (lane == 0) ptx::mbar_wait(&ctl->item_bar[k & 3u], (k >> 2) & 1u);
+                __syncwarp();
+                id = ctl->item_id[k & 3u];
+            } else {
+                id = item_at(k, total);
+            }
             if (id < 0) break;
             const Item I = item_geom(G, id);
             uint32_t *thr_cur = ctl->thr_sh[k & 1u];
@@ -194,7 +241,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
             const int c_lo = qcol - G.radius;
             const int c_lo_cl = max(c_lo, 0), c_hi_cl = min(qcol + G.radius, G.W - 1);
-            float thr = -INFINITY;
+            float thr = (G.flags & 2) ? INFINITY : -INFINITY;      // debug flags (TIMET_TC_PFLAGS): 1 no scan, 2 scan without appends, 4 TMEM loads only
             int cnt = 0, lost = 0;
 
             // first tile of this item that lands in my buffer: (gtile + j) % nbuf == mybuf
@@ -205,16 +252,18 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (; j < I.ntiles; j += G.nbuf, ++use) {
                 const int kr_start = I.kr_lo + ch * G.RPC;
                 const int rc = min(G.RPC, I.kr_hi + 1 - kr_start);
-                if (lane == 0) ptx::mbar_wait(&ctl->tmem_full[mybuf], use & 1u);
+                if (lane == 0) { if (G.flags & 32) ptx::mbar_wait_sleep(&ctl->tmem_full[mybuf], use & 1u, 64); else ptx::mbar_wait(&ctl->tmem_full[mybuf], use & 1u); }
                 __syncwarp();
                 ptx::tc_fence_after();
                 thr = fmaxf(thr, thr_dec(thr_cur[qi]));
-                for (int rr = 0; rr < rc; ++rr) {
+                for (int rr = 0; rr < ((G.flags & 1) ? 0 : rc); ++rr) {
                     if (row_par >= 0 && (rr & 1) != row_par) continue;
                     const int kr = kr_start + rr;
                     const bool row_ok = valid && kr >= r_lo && kr <= r_hi;
                     if (!__any_sync(0xffffffffu, row_ok)) continue;
-                    const int code_row = (ci << 10) | ((kr - r_lo) << 5);
+                    // pick up the other groups' progress (one LDS per key row): the four groups of a query raise one threshold
+                    if (!(G.flags & 64)) thr = fmaxf(thr, thr_dec(thr_cur[qi]));
+                    const int code_row = (((G.flags & 8) ? ci : I.nctx - 1 - ci) << 10) | ((kr - r_lo) << 5);
                     for (int cb = 0; cb < G.W; cb += 16) {
                         int col0 = rr * G.W + cb;
                         const int shift = max(0, col0 + 16 - G.buf_cols);
@@ -228,6 +277,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         const uint32_t code0 = (uint32_t)(code_row + (cb_eff - c_lo));
                         uint32_t slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
                         ptx::tmem_ld_wait();
+                        if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[5]), "r"(r[10]), "r"(r[15])); continue; }
 #define TC_OFFER(E) tc_offer<(1u << (E))>(slot, __uint_as_float(r[E]), thr, wmask, code0 + (E));
                         TC_OFFER(0) TC_OFFER(1) TC_OFFER(2) TC_OFFER(3) TC_OFFER(4) TC_OFFER(5) TC_OFFER(6) TC_OFFER(7)
                         TC_OFFER(8) TC_OFFER(9) TC_OFFER(10) TC_OFFER(11) TC_OFFER(12) TC_OFFER(13) TC_OFFER(14) TC_OFFER(15)
@@ -297,7 +347,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<512>(tmem_base);
     }
@@ -313,6 +363,7 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
     TcGeom G;
     if (!tc_geometry(p, L, &G)) return TIMET_ERR_UNSUPPORTED;
     G.nstages = TC_MAX_STAGES;
+    { const char *pf = getenv("TIMET_TC_PFLAGS"); G.flags = pf ? atoi(pf) : 0; }
     const char *ns = getenv("TIMET_TC_STAGES");
     if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G.nstages = atoi(ns);
     while (persist_smem_bytes(G) > 227 * 1024 && G.nstages > 2) G.nstages--;
@@ -323,10 +374,12 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
     if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
     if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
     const size_t smem = persist_smem_bytes(G);
-    TIMET_CUDA(cudaFuncSetAttribute(ff_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const char *dy = getenv("TIMET_TC_DYN");
+    auto kern = (dy && dy[0] == '0') ? ff_tc_persist_kernel<false> : ff_tc_persist_kernel<true>;
+    TIMET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = G.total_tiles < num_sms() ? G.total_tiles : num_sms();
     unsigned int *next_item = reinterpret_cast<unsigned int *>(ws + L.off_redo + 128);   // zeroed with the redo header by timet_ff_select
-    ff_tc_persist_kernel<<<(unsigned)grid, TC_THREADS, smem, st>>>(map_a, map_b, G, reinterpret_cast<uint32_t *>(ws + L.off_cand),
+    kern<<<(unsigned)grid, TC_THREADS, smem, st>>>(map_a, map_b, G, reinterpret_cast<uint32_t *>(ws + L.off_cand),
                                                                   reinterpret_cast<uint32_t *>(ws + L.off_cand_meta), next_item);
     TIMET_LAUNCHED();
     return TIMET_OK;

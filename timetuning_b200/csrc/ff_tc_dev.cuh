@@ -90,21 +90,18 @@ __device__ __forceinline__ void tc_filter(uint32_t list, int &cnt, float thr) {
 }
 
 // Raise thr from the list content and drop entries that can no longer be among the top-k.
-// One pass over the list keeps the 8 largest packed entries in sorted registers (max/min chain), so the
-// k-th largest (k <= 8) is read off directly.  Warp-synchronous; loop bounds are warp-uniform.
-// Afterwards cnt <= keep_max (entries beyond that are dropped and the query is flagged for the exact re-do).
-__device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, int &lost, int k, int keep_max) {
-    int maxcnt = cnt;
+// One pass over the list keeps the KK largest packed entries in sorted registers (max/min chain), so the
+// k-th largest (k <= KK) is read off directly.  Warp-synchronous; loop bounds are warp-uniform.
+template <int KK>
+__device__ __forceinline__ uint32_t tc_kth_largest(uint32_t list, int cnt, int maxcnt, int k) {
+    uint32_t top[KK];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
-    uint32_t top[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) top[j] = 0u;
+    for (int j = 0; j < KK; ++j) top[j] = 0u;
 #pragma unroll 4
     for (int s = 0; s < maxcnt; ++s) {
         uint32_t e = (s < cnt) ? lds_u32(list + s * TC_SLOT_STRIDE) : 0u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < KK; ++j) {
             const uint32_t hi = max(e, top[j]);
             e = min(e, top[j]);
             top[j] = hi;
@@ -112,7 +109,17 @@ __device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, 
     }
     uint32_t kth = top[0];
 #pragma unroll
-    for (int j = 1; j < 8; ++j) kth = (k - 1 == j) ? top[j] : kth;
+    for (int j = 1; j < KK; ++j) kth = (k - 1 == j) ? top[j] : kth;
+    return kth;
+}
+
+// Afterwards cnt <= keep_max (entries beyond that are dropped and the query is flagged for the exact re-do).
+__device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, int &lost, int k, int keep_max) {
+    int maxcnt = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
+    // the chain costs 2 instructions per (entry, register): the usual k = 5 gets a 5-deep chain
+    const uint32_t kth = (k <= 5) ? tc_kth_largest<5>(list, cnt, maxcnt, k) : tc_kth_largest<8>(list, cnt, maxcnt, k);
     if (kth != 0u) thr = fmaxf(thr, tc_decode(kth) - FF_TC_SLACK);
     tc_filter(list, cnt, thr);
     if (cnt > keep_max) { cnt = keep_max; lost = 1; }

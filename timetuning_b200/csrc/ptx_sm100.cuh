@@ -56,6 +56,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         }
     }
 }
+// Polite variant for many-waiter barriers: sleeps between polls so that the pollers leave the issue slots to the others
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++spins > (1u << 22)) {
+            printf("timet: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+                   (void *)bar, parity);
+            __trap();
+        }
+    }
+}
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {
