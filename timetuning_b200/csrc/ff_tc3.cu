@@ -222,6 +222,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t list0 = ptx::smem_u32(sList + qi);
         const uint32_t list = list0 + (uint32_t)g * TC_CAP * 128u * 4u;
         constexpr int half = TC_CAP / 2;
+        const uint32_t slot_lim = list + (uint32_t)(TC_CAP - 8) * TC_SLOT_STRIDE;   // compaction trigger: more than 24 entries
         const uint32_t t_acc = tmem_base + (uint32_t)(mybuf * G.buf_cols) + lane_base;
         uint32_t gtile = 0;                                            // tiles issued before this item (all roles agree)
         for (uint32_t k = 0;; ++k) {
@@ -278,16 +279,24 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                         uint32_t slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
                         ptx::tmem_ld_wait();
                         if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[5]), "r"(r[10]), "r"(r[15])); continue; }
-#define TC_OFFER(E) tc_offer<(1u << (E))>(slot, __uint_as_float(r[E]), thr, wmask, code0 + (E));
-                        TC_OFFER(0) TC_OFFER(1) TC_OFFER(2) TC_OFFER(3) TC_OFFER(4) TC_OFFER(5) TC_OFFER(6) TC_OFFER(7)
-                        TC_OFFER(8) TC_OFFER(9) TC_OFFER(10) TC_OFFER(11) TC_OFFER(12) TC_OFFER(13) TC_OFFER(14) TC_OFFER(15)
-#undef TC_OFFER
+                        // two runs of 8 offers, each followed by a capacity check: a list holds TC_CAP = 32 entries and at
+                        // most 24 when a run starts (compaction leaves <= 16), so a run can never overflow it
+#define TC_CHECK()                                                                       \
+    if (__any_sync(0xffffffffu, slot > slot_lim)) {                                      \
+        const float before = thr;                                                        \
+        cnt = (int)((slot - list) / TC_SLOT_STRIDE);                                     \
+        tc_compact(list, cnt, thr, lost, G.topk, half);                                  \
+        slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;                                    \
+        if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));                         \
+    }
+                        tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
+                        tc_offer4<4>(slot, r[4], r[5], r[6], r[7], thr, wmask, code0);
+                        TC_CHECK()
+                        tc_offer4<8>(slot, r[8], r[9], r[10], r[11], thr, wmask, code0);
+                        tc_offer4<12>(slot, r[12], r[13], r[14], r[15], thr, wmask, code0);
+                        TC_CHECK()
+#undef TC_CHECK
                         cnt = (int)((slot - list) / TC_SLOT_STRIDE);
-                        if (__any_sync(0xffffffffu, cnt > half)) {
-                            const float before = thr;
-                            tc_compact(list, cnt, thr, lost, G.topk, half);
-                            if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));
-                        }
                     }
                 }
                 ptx::tc_fence_before();

@@ -72,6 +72,54 @@ __device__ __forceinline__ void tc_offer(uint32_t &slot_addr, float v, float thr
         : "memory");
 }
 
+// Four epilogue steps (elements E .. E+3 of a 16-column TMEM block) in ONE asm statement: ptxas may interleave the four
+// window-test -> compare -> append chains, which a sequence of volatile single-step statements forbids.
+template <uint32_t E>
+__device__ __forceinline__ void tc_offer4(uint32_t &slot_addr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, float thr,
+                                          uint32_t wmask, uint32_t code0) {
+    // the packed candidate is computed unconditionally (FADD + IMAD on the FMA pipe); only the store and the slot advance
+    // are predicated.  Predicated writes to the temporaries would make ptxas carry their old values around (SEL / MOV).
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b32 m0, m1, m2, m3, x0, x1, x2, x3, y0, y1, y2, y3;\n\t.reg .f32 t0, t1, t2, t3;\n\t"
+        "and.b32 m0, %6, %8;\n\t"
+        "and.b32 m1, %6, %9;\n\t"
+        "and.b32 m2, %6, %10;\n\t"
+        "and.b32 m3, %6, %11;\n\t"
+        "setp.ne.b32 p0, m0, 0;\n\t"
+        "setp.ne.b32 p1, m1, 0;\n\t"
+        "setp.ne.b32 p2, m2, 0;\n\t"
+        "setp.ne.b32 p3, m3, 0;\n\t"
+        "setp.gt.and.f32 p0, %1, %5, p0;\n\t"
+        "setp.gt.and.f32 p1, %2, %5, p1;\n\t"
+        "setp.gt.and.f32 p2, %3, %5, p2;\n\t"
+        "setp.gt.and.f32 p3, %4, %5, p3;\n\t"
+        "add.rn.f32 t0, %1, 0f42840000;\n\t"     // + 66.0f
+        "add.rn.f32 t1, %2, 0f42840000;\n\t"
+        "add.rn.f32 t2, %3, 0f42840000;\n\t"
+        "add.rn.f32 t3, %4, 0f42840000;\n\t"
+        "mov.b32 x0, t0;\n\t"
+        "mov.b32 x1, t1;\n\t"
+        "mov.b32 x2, t2;\n\t"
+        "mov.b32 x3, t3;\n\t"
+        "mad.lo.u32 y0, x0, 8192, %7;\n\t"
+        "mad.lo.u32 y1, x1, 8192, %12;\n\t"
+        "mad.lo.u32 y2, x2, 8192, %13;\n\t"
+        "mad.lo.u32 y3, x3, 8192, %14;\n\t"
+        "@p0 st.shared.u32 [%0], y0;\n\t"
+        "@p0 add.u32 %0, %0, 512;\n\t"
+        "@p1 st.shared.u32 [%0], y1;\n\t"
+        "@p1 add.u32 %0, %0, 512;\n\t"
+        "@p2 st.shared.u32 [%0], y2;\n\t"
+        "@p2 add.u32 %0, %0, 512;\n\t"
+        "@p3 st.shared.u32 [%0], y3;\n\t"
+        "@p3 add.u32 %0, %0, 512;\n\t}"
+        : "+r"(slot_addr)
+        : "f"(__uint_as_float(v0)), "f"(__uint_as_float(v1)), "f"(__uint_as_float(v2)), "f"(__uint_as_float(v3)), "f"(thr),
+          "r"(wmask), "r"(code0 + E), "n"(1u << E), "n"(2u << E), "n"(4u << E), "n"(8u << E), "r"(code0 + E + 1),
+          "r"(code0 + E + 2), "r"(code0 + E + 3)
+        : "memory");
+}
+
 // Drop entries below thr.  Warp-synchronous (loop bound = warp max of cnt).
 __device__ __forceinline__ void tc_filter(uint32_t list, int &cnt, float thr) {
     int maxcnt = cnt;
