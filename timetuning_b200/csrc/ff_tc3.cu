@@ -94,6 +94,10 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int W_PROD = 16, W_MMA = 17, W_ALLOC = 18, W_INIT = 19;
     const int64_t total = G.total_tiles;          // work items = query tiles
+    // Every key tile is scanned by ALL four epilogue groups (key rows dealt round-robin), not by the two groups that own
+    // its TMEM buffer: a buffer is released after a quarter of the per-warp work instead of half, and 16 instead of 8
+    // warps hide each other's latencies while the MMA warp fills the other buffer.  flags & 128: old mapping.
+    const bool share_tiles = G.nbuf == 2 && !(G.flags & 128);
 
     if (warp == W_PROD && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -104,7 +108,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         ptx::mbar_init(&ctl->a_full, 1);
         ptx::mbar_init(&ctl->a_free, 1);
         for (int i = 0; i < 4; ++i) ptx::mbar_init(&ctl->item_bar[i], 1);
-        for (int b = 0; b < G.nbuf; ++b) { ptx::mbar_init(&ctl->tmem_full[b], 1); ptx::mbar_init(&ctl->tmem_empty[b], G.nbuf == 4 ? 4 : 8); }
+        for (int b = 0; b < G.nbuf; ++b) { ptx::mbar_init(&ctl->tmem_full[b], 1); ptx::mbar_init(&ctl->tmem_empty[b], share_tiles ? 16 : (G.nbuf == 4 ? 4 : 8)); }
         ptx::fence_barrier_init();
     }
     if (warp == W_ALLOC) ptx::tmem_alloc<512>(&ctl->tmem_base);
@@ -223,7 +227,6 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t list = list0 + (uint32_t)g * TC_CAP * 128u * 4u;
         constexpr int half = TC_CAP / 2;
         const uint32_t slot_lim = list + (uint32_t)(TC_CAP - 8) * TC_SLOT_STRIDE;   // compaction trigger: more than 24 entries
-        const uint32_t t_acc = tmem_base + (uint32_t)(mybuf * G.buf_cols) + lane_base;
         uint32_t gtile = 0;                                            // tiles issued before this item (all roles agree)
         for (uint32_t k = 0;; ++k) {
             int64_t id;
@@ -246,19 +249,23 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int cnt = 0, lost = 0;
 
             // first tile of this item that lands in my buffer: (gtile + j) % nbuf == mybuf
-            int j = (int)(((uint32_t)mybuf + (uint32_t)G.nbuf - (gtile % (uint32_t)G.nbuf)) % (uint32_t)G.nbuf);
+            int j = share_tiles ? 0 : (int)(((uint32_t)mybuf + (uint32_t)G.nbuf - (gtile % (uint32_t)G.nbuf)) % (uint32_t)G.nbuf);
+            const int jstep = share_tiles ? 1 : G.nbuf;
             int ci = 0, ch = j;
             while (ch >= I.nchunks) { ch -= I.nchunks; ++ci; }
-            uint32_t use = (gtile + (uint32_t)j) / (uint32_t)G.nbuf;
-            for (; j < I.ntiles; j += G.nbuf, ++use) {
+            for (; j < I.ntiles; j += jstep) {
                 const int kr_start = I.kr_lo + ch * G.RPC;
                 const int rc = min(G.RPC, I.kr_hi + 1 - kr_start);
-                if (lane == 0) { if (G.flags & 32) ptx::mbar_wait_sleep(&ctl->tmem_full[mybuf], use & 1u, 64); else ptx::mbar_wait(&ctl->tmem_full[mybuf], use & 1u); }
+                const uint32_t tile_no = gtile + (uint32_t)j;                      // running tile count of this CTA
+                const int buf = share_tiles ? (int)(tile_no & 1u) : mybuf;
+                const uint32_t use = tile_no / (uint32_t)G.nbuf;
+                const uint32_t t_acc = tmem_base + (uint32_t)(buf * G.buf_cols) + lane_base;
+                if (lane == 0) { if (G.flags & 32) ptx::mbar_wait_sleep(&ctl->tmem_full[buf], use & 1u, 64); else ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u); }
                 __syncwarp();
                 ptx::tc_fence_after();
                 thr = fmaxf(thr, thr_dec(thr_cur[qi]));
                 for (int rr = 0; rr < ((G.flags & 1) ? 0 : rc); ++rr) {
-                    if (row_par >= 0 && (rr & 1) != row_par) continue;
+                    if (share_tiles ? ((rr & 3) != g) : (row_par >= 0 && (rr & 1) != row_par)) continue;
                     const int kr = kr_start + rr;
                     const bool row_ok = valid && kr >= r_lo && kr <= r_hi;
                     if (!__any_sync(0xffffffffu, row_ok)) continue;
@@ -301,8 +308,8 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[mybuf]);
-                ch += G.nbuf;
+                if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[buf]);
+                ch += jstep;
                 while (ch >= I.nchunks) { ch -= I.nchunks; ++ci; }
             }
             gtile += (uint32_t)I.ntiles;
