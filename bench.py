@@ -304,14 +304,14 @@ def main():
                 rows = min(sr - 1, qr1 + CFG["radius"]) - max(0, qr0 - CFG["radius"]) + 1
                 exec_flops += 2.0 * 128 * rows * W_ * D
             exec_flops *= sigma_ctx * bs
-            roof = {"bound": "tensor", "kernel": "ff_tc_kernel (tcgen05 affinity + fused window / top-k nomination), "
+            roof = {"bound": "tensor", "kernel": "ff_tc_persist_kernel (tcgen05 affinity + fused window / top-k nomination), "
                     "timed alone with CUDA events recorded by the library around its launch",
                     "achieved": dense_flops / (tc_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                     "flops_model": "dense 2*N^2*D*sum_ctx per clip (SURVEY.md §8d) x clips per launch",
                     "executed_tflops": exec_flops / (tc_ms * 1e-3) / 1e12, "executed_over_dense": exec_flops / dense_flops,
                     "ms_per_launch": tc_ms,
-                    "traffic": 162.8e6, "traffic_source": "ncu --set full, profiles/r1_ncu_full_kernels.md: dram read 154.2 MB + write 8.6 MB per launch"}
+                    "traffic": 161.9e6, "traffic_source": "ncu --set full, profiles/r1_ncu_full_kernels.md: dram read 154.5 MB + write 7.4 MB per launch"}
         else:
             roof = {"bound": "tensor", "kernel": "ff_select_exact (fp32 CUDA-core scan; tensor-core engine not used)",
                     "achieved": dense_flops / (stage_ms["select"] * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",

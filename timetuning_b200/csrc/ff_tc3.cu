@@ -19,8 +19,13 @@
 // is a function of blockIdx and kernel parameters only) and elect one lane per TMA / MMA / commit.  With a divergent
 // `if (lane == 0)` around the loops ptxas cannot keep descriptors in uniform registers and wraps every UTCHMMA / UTMALDG
 // in an ELECT + 7 x R2UR "waterfall" (about 100 scalar instructions per 64-wide K chunk, more than the 504 cycles the
-// four MMAs of the chunk take): the tensor pipe then idles on instruction issue.  Both warps also take the HIGHEST warp
-// ids, which the SMSP arbiter favours over the 16 epilogue warps.
+// four MMAs of the chunk take): the tensor pipe then idles on instruction issue (MMA/TMA side alone 0.31 -> 0.245 ms at
+// BASELINE configs[1]).  Warp ids: epilogue 0-15 (TMEM lane quadrant = warp & 3), producer 16, MMA 17; giving the issue warps
+// the highest ids (which the SMSP arbiter favours) made no measurable difference.
+//
+// TIMET_TC_PFLAGS (attribution switches, profiles/tc_kernel_time.py): 1 release tiles unscanned, 2 scan without appends,
+// 4 TMEM loads only, 8 oldest-first context order, 32 nanosleep back-off while polling tmem_full, 64 shared threshold read
+// once per tile instead of once per key row, 128 each TMEM buffer scanned by its own two groups only.
 #include <stdlib.h>
 
 #include "ff_tc_dev.cuh"
@@ -97,7 +102,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // Every key tile is scanned by ALL four epilogue groups (key rows dealt round-robin), not by the two groups that own
     // its TMEM buffer: a buffer is released after a quarter of the per-warp work instead of half, and 16 instead of 8
     // warps hide each other's latencies while the MMA warp fills the other buffer.  flags & 128: old mapping.
-    const bool share_tiles = G.nbuf == 2 && !(G.flags & 128);
+    const bool share_tiles = !(G.flags & 128);
 
     if (warp == W_PROD && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -257,7 +262,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int kr_start = I.kr_lo + ch * G.RPC;
                 const int rc = min(G.RPC, I.kr_hi + 1 - kr_start);
                 const uint32_t tile_no = gtile + (uint32_t)j;                      // running tile count of this CTA
-                const int buf = share_tiles ? (int)(tile_no & 1u) : mybuf;
+                const int buf = share_tiles ? (int)(tile_no % (uint32_t)G.nbuf) : mybuf;
                 const uint32_t use = tile_no / (uint32_t)G.nbuf;
                 const uint32_t t_acc = tmem_base + (uint32_t)(buf * G.buf_cols) + lane_base;
                 if (lane == 0) { if (G.flags & 32) ptx::mbar_wait_sleep(&ctl->tmem_full[buf], use & 1u, 64); else ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u); }
