@@ -243,14 +243,25 @@ __global__ void sk_fill(float *p, int n, float v) {
 // (bit-reproducible, identical on every CTA).
 constexpr int SKR_THREADS = 1024;
 constexpr int SKR_WARPS = SKR_THREADS / 32;
-constexpr int SKR_RED = 8;            // rows of the cross-warp reduction scratch (warps fold in SKR_WARPS / SKR_RED rounds)
+constexpr int SKR_RED = 16;           // rows of the cross-warp reduction scratch (warps fold in SKR_WARPS / SKR_RED rounds)
+// Every CTA adds its K marginal partials to K global fixed-point accumulators per iteration.  Packed, the 200 accumulators
+// of config 2 share 13 cache lines and the 29 600 atomics of an iteration serialise in a handful of L2 slices; with one
+// accumulator per 256 B (the granularity of the address -> L2 slice hash) they spread over all slices.
+constexpr int SKR_USTRIDE = 32;
+// An accumulator is (fixed-point sum << 16) | arrivals: one atomicAdd delivers a CTA's partial AND its arrival, and every
+// CTA polls the K accumulators themselves until all CTAs are in -- no separate grid barrier (bar.sync + release fence +
+// counter + re-read) inside the iteration loop.  The two buffers alternate by iteration parity and are never reset
+// during a call: the marginal of iteration `it` is the difference to the value read two iterations earlier.
+constexpr int SKR_CNT_BITS = 16;
 
 struct SkResArgs {
     const float *in;
     float *q_out;
     float *partials;          // [2, grid, K]
     unsigned int *bar;        // monotonic grid-barrier counter (zeroed before launch)
-    unsigned long long *ufix; // [3, K] fixed-point marginal accumulators (zeroed before launch)
+    unsigned long long *ufix; // [2, K * ustride] fixed-point marginal accumulators with arrival counts (zeroed before launch)
+    float ufix_scale, ufix_inv; // 2^sbits and 2^-sbits of the fixed-point part
+    int ustride;              // u64 elements between two accumulators (SKR_USTRIDE: every accumulator in its own 256 B L2 block)
     void *const *peers;       // world_size > 1: every rank's P2PBuf (NVLink peer memory), else nullptr
     int rank, ws;
     unsigned long long epoch0; // exchanges completed before this call (same on every rank)
@@ -381,6 +392,7 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) a_s[i] = __fdiv_rn(A.r, a_s[i]);
     __syncthreads();
 
+    unsigned long long prev0 = 0ull, prev1 = 0ull;                    // accumulator values read at the previous even / odd iteration
     for (int it = 0; it < A.iters; ++it) {
         float4 av[NV4];
 #pragma unroll
@@ -390,57 +402,89 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
             acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const bool last = (it == A.iters - 1);
-        // ---- sweep the resident rows: s_j = sum_i a_i E_ji ; then either u_i += a_i E_ji * c/s_j or write Q
-        for (int rl = warp; rl < nrows; rl += SKR_WARPS) {
-            float4 p[NV4];
-            float s = 0.f;
+        // ---- sweep the resident rows: s_j = sum_i a_i E_ji ; then either u_i += a_i E_ji * c/s_j or write Q.
+        // Two rows of a warp are in flight together (their load -> multiply -> butterfly -> divide chains are
+        // independent); rows still enter acc in ascending order, so the sums are the same bit for bit.
+        constexpr int RPW = (NV4 <= 2) ? 2 : 1;           // wider rows (K > 256) would spill with two rows in registers
+        for (int rl = warp; rl < nrows; rl += RPW * SKR_WARPS) {
+            const int rl2 = rl + SKR_WARPS;
+            const bool two = RPW == 2 && rl2 < nrows;
+            float4 p[NV4], q[NV4];
+            float s = 0.f, s2 = 0.f;
 #pragma unroll
             for (int v = 0; v < NV4; ++v) {
                 const int i4 = lane + 32 * v;
                 const float4 e = (i4 < K4) ? E[(size_t)rl * K4 + i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 f = (two && i4 < K4) ? E[(size_t)rl2 * K4 + i4] : make_float4(0.f, 0.f, 0.f, 0.f);
                 p[v] = make_float4(e.x * av[v].x, e.y * av[v].y, e.z * av[v].z, e.w * av[v].w);
+                q[v] = make_float4(f.x * av[v].x, f.y * av[v].y, f.z * av[v].z, f.w * av[v].w);
                 s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
+                s2 += (q[v].x + q[v].y) + (q[v].z + q[v].w);
             }
-            s = warp_sum(s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
             if (!last) {
                 const float b = __fdiv_rn(A.c, s);
+                const float b2 = two ? __fdiv_rn(A.c, s2) : 0.f;
 #pragma unroll
                 for (int v = 0; v < NV4; ++v) {
                     acc[v].x = fmaf(p[v].x, b, acc[v].x); acc[v].y = fmaf(p[v].y, b, acc[v].y);
                     acc[v].z = fmaf(p[v].z, b, acc[v].z); acc[v].w = fmaf(p[v].w, b, acc[v].w);
                 }
+                if (two) {
+#pragma unroll
+                    for (int v = 0; v < NV4; ++v) {
+                        acc[v].x = fmaf(q[v].x, b2, acc[v].x); acc[v].y = fmaf(q[v].y, b2, acc[v].y);
+                        acc[v].z = fmaf(q[v].z, b2, acc[v].z); acc[v].w = fmaf(q[v].w, b2, acc[v].w);
+                    }
+                }
             } else {
                 const float inv = __fdiv_rn(1.f, s);
+                const float inv2 = two ? __fdiv_rn(1.f, s2) : 0.f;
                 float4 *dst = reinterpret_cast<float4 *>(A.q_out + (row0 + rl) * K);
+                float4 *dst2 = reinterpret_cast<float4 *>(A.q_out + (row0 + rl2) * K);
 #pragma unroll
                 for (int v = 0; v < NV4; ++v) {
                     const int i4 = lane + 32 * v;
                     if (i4 < K4) __stcs(dst + i4, make_float4(p[v].x * inv, p[v].y * inv, p[v].z * inv, p[v].w * inv));
+                    if (two && i4 < K4) __stcs(dst2 + i4, make_float4(q[v].x * inv2, q[v].y * inv2, q[v].z * inv2, q[v].w * inv2));
                 }
             }
         }
         if (last) break;
-        // ---- marginals of Q itself, u_i = sum_j a_i E_ji b_j (they sum to 1 over i, so 2^-62 fixed point never
+        // ---- marginals of Q itself, u_i = sum_j a_i E_ji b_j (they sum to 1 over i, so the fixed point never
         // overflows): integer atomics are associative -> the grid-wide sum is bit-reproducible without a fold.
+        // The add carries the arrival (+1 in the low 16 bits); each column's thread polls its own accumulator.
         skr_fold_warps<NV4>(red, acc, K, K4, warp, lane);
-        unsigned long long *ufix = A.ufix + (size_t)(it % 3) * K;
-        for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
+        unsigned long long *ufix = A.ufix + (size_t)(it & 1) * K * A.ustride;
+        const unsigned long long want = (unsigned long long)((it >> 1) + 1) * gridDim.x;     // arrivals after this iteration
+        float u_mine = 0.f;
+        const int i = threadIdx.x;                                    // K <= 512 < SKR_THREADS: one column per thread
+        if (i < K) {
             float t = 0.f;
 #pragma unroll
             for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
-            atomicAdd(ufix + i, (unsigned long long)__float2ll_rn(t * 4611686018427387904.0f));
+            unsigned long long *acc_i = ufix + (size_t)i * A.ustride;
+            atomicAdd(acc_i, ((unsigned long long)__float2ll_rn(t * A.ufix_scale) << SKR_CNT_BITS) + 1ull);
+            unsigned long long v;
+            unsigned int spins = 0;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(acc_i) : "memory");
+                if (++spins > (1u << 24)) { printf("timet: sinkhorn marginal wait timed out (block %d column %d iteration %d)\n", (int)blockIdx.x, i, it); __trap(); }
+            } while ((v & ((1ull << SKR_CNT_BITS) - 1ull)) < want);
+            const unsigned long long cur = v >> SKR_CNT_BITS;
+            const unsigned long long prev = (it & 1) ? prev1 : prev0;
+            u_mine = (float)((double)(long long)(cur - prev) * (double)A.ufix_inv);            // local u_i
+            if (it & 1) prev1 = cur; else prev0 = cur;
         }
-        grid_barrier(A.bar, (++epoch) * gridDim.x);
-        for (int i = threadIdx.x; i < K; i += SKR_THREADS)
-            red[i] = (float)((double)(long long)__ldcg(ufix + i) * 2.168404344971009e-19);      // local u_i (* 2^-62)
+        __syncthreads();                                               // everyone is done with the fold scratch
+        if (i < K) red[i] = u_mine;
         __syncthreads();
         if (A.ws > 1) skr_exchange(A, xch++, red);                     // u_i summed over ranks (my_utils.py:270-272)
-        for (int i = threadIdx.x; i < K; i += SKR_THREADS)
-            a_s[i] = a_s[i] * __fdiv_rn(A.r, red[i]);                  // Q *= r / u  (my_utils.py:268)
-        if (blockIdx.x == 0) {                                         // recycle the buffer of iteration it-1 for it+2
-            unsigned long long *z = A.ufix + (size_t)((it + 2) % 3) * K;
-            for (int i = threadIdx.x; i < K; i += SKR_THREADS) z[i] = 0ull;
-        }
+        if (i < K) a_s[i] = a_s[i] * __fdiv_rn(A.r, red[i]);           // Q *= r / u  (my_utils.py:268)
         __syncthreads();
     }
 }
@@ -511,7 +555,7 @@ size_t timet_sinkhorn_workspace_bytes(int64_t B, int K) {
     (void)B;
     if (K < 1) return 0;
     const size_t grid_max = 2 * 160;   // >= 2 * SM count on every B200 SKU
-    return align_up((grid_max + 2) * (size_t)K * sizeof(float) + 256 + 3 * (size_t)K * sizeof(unsigned long long) + 64, 256);
+    return align_up((grid_max + 2) * (size_t)K * sizeof(float) + 512 + 2 * (size_t)K * SKR_USTRIDE * sizeof(unsigned long long) + 64, 256);
 }
 
 int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
@@ -537,14 +581,23 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
         unsigned long long *pepoch = nullptr;
         const bool p2p = world_size > 1 && comm_p2p_info(comm, &peers, &prank, &pws, &pepoch) && pws == world_size && K <= P2P_MAX_K;
         if ((world_size == 1 || p2p) && iters >= 1 && !(force && force[0] == '1') && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
-            (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160) {
+            (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160 &&
+            (int64_t)(iters / 2 + 1) * rgrid < (1 << SKR_CNT_BITS)) {      // arrival counts of a call fit their 16 bits
             float *partials = (float *)workspace;
             unsigned int *bar = (unsigned int *)(partials + (size_t)322 * K);
             // bar (64 B slot) followed by the 8-byte aligned fixed-point buffers; one memset clears both
             const size_t bar_off = (size_t)322 * K * sizeof(float);
-            const size_t ufix_off = align_up(bar_off + 64, 64);
-            TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 3 * (size_t)K * sizeof(unsigned long long), st));
+            const size_t ufix_off = align_up(bar_off + 64, 256);
+            const char *us = getenv("TIMET_SK_USTRIDE");        // 1 = packed accumulators (for comparison)
+            const int ustride = (us && atoi(us) >= 1 && atoi(us) <= SKR_USTRIDE) ? atoi(us) : SKR_USTRIDE;
+            TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
             SkResArgs R;
+            R.ustride = ustride;
+            // 48 data bits: the marginals of one iteration sum to <= 1 and a buffer accumulates ceil(iters / 2) of them
+            int head = 1;
+            while ((1 << head) < iters / 2 + 2) ++head;
+            R.ufix_scale = ldexpf(1.0f, 47 - head);
+            R.ufix_inv = ldexpf(1.0f, head - 47);
             R.ufix = (unsigned long long *)((char *)workspace + ufix_off);
             R.in = in; R.q_out = q_out; R.partials = partials; R.bar = bar; R.B = B; R.K = K; R.iters = iters;
             R.rows_per_cta = rpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
