@@ -128,3 +128,30 @@ def test_tc_random_features_worst_case():
     for (c, t), (w, k, n) in ref.items():
         w2, k2, n2 = plan.selection(c, t)
         assert torch.equal(n, n2) and torch.equal(k, k2) and torch.equal(w, w2), (c, t)
+
+
+@pytest.mark.parametrize("env", [
+    {"TIMET_TC_PERSIST": "0"},                  # one CTA per work item (ff_tc.cu)
+    {"TIMET_TC_PAIR": "1"},                     # CTA pairs, cta_group::2 (ff_tc2.cu)
+    {"TIMET_TC_DYN": "0"},                      # persistent kernel, static snake schedule
+    {"TIMET_TC_NBUF": "4"},                     # four 128-column TMEM buffers
+    {"TIMET_TC_PFLAGS": "128"},                 # every TMEM buffer scanned by its own two groups
+    {"TIMET_TC_PFLAGS": "72"},                  # oldest-first contexts, threshold picked up per tile
+], ids=lambda e: "+".join(f"{k[9:]}={v}" for k, v in e.items()))
+def test_tc_kernel_variants_are_bit_identical(monkeypatch, env):
+    """Every kernel variant / schedule behind the experiment switches nominates a superset of the exact
+    top-k, so after the fp32 re-evaluation all of them reproduce the exact engine bit for bit."""
+    bs, fs, sr, D = 3, 8, 28, 384
+    feats = torch.from_numpy(synth.clip_features(bs, fs, sr, D, seed=5)).cuda()
+    plan = tb.FFPlan(bs, fs, sr, sr, D, 8, 7, 6, 5)
+    plan.prepare(feats)
+    plan.select(tb.FF_EXACT)
+    ref = {(c, t): [x.clone() for x in plan.selection(c, t)] for c in range(bs) for t in range(1, fs)}
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    plan.select(tb.FF_TC)
+    st = plan.stats()
+    for (c, t), (w, k, n) in ref.items():
+        w2, k2, n2 = plan.selection(c, t)
+        assert torch.equal(n, n2) and torch.equal(k, k2) and torch.equal(w, w2), (env, c, t)
+    assert st["redone_queries"] <= 0.02 * st["queries"], st
