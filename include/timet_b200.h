@@ -45,6 +45,9 @@ const char *timet_last_error(void);
 int timet_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 int64_t timet_launch_count(void);
+/* The experiment / debug switches (environment variables TIMET_*) are read once, at first use; this
+ * re-reads them (tests flip switches inside one process).  Not needed in production. */
+int timet_debug_reload_env(void);
 
 /* ------------------------------------------------------------------ Sinkhorn-Knopp
  * Stands behind  my_utils.sinkhorn(Q, nmb_iters, world_size)      my_utils.py:246-274
@@ -136,7 +139,14 @@ int timet_ff_propagate(const timet_ff_params *p, int engine, const float *feats,
 /* Diagnostics of the last timet_ff_select on this workspace (device -> 8 x int64 at `out`, device ptr):
  * [0] queries, [1] selected (weight) entries, [2] queries with more than topk entries (exact ties),
  * [3] TC candidates nominated, [4] queries re-done by the exact scan (candidate-list overflow),
- * [5] queries whose tie set was truncated, [6..7] reserved. */
+ * [5] queries whose tie set was TRUNCATED to the kw slots because the wide-row pool was exhausted (0 unless more
+ *     than ~4 entries per query on average are needed; the Python shims raise when it is non-zero),
+ * [6] wide rows (queries with more than kw survivors, kept completely in the pool), [7] reserved.
+ *
+ * Ties.  The reference keeps EVERY key whose affinity equals the k-th largest (mask_propagation.py:432-436), so a
+ * query can have more than topk weights -- clips with repeated frames (data_loader.py:621-623) produce exact ties
+ * across contexts.  Up to kw = timet_ff_slots(p) survivors live in the regular slots; larger sets are stored as
+ * variable-length "wide rows": counts[i] = -n and keys[i * kw] = offset of the row's n entries in the pool. */
 int timet_ff_stats(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int64_t *out,
                    timet_stream_t stream);
 /* Copy the sparse selection of (clip, t) out of the workspace for inspection / tests:
@@ -145,6 +155,10 @@ int timet_ff_stats(const timet_ff_params *p, const void *workspace, size_t works
 int timet_ff_slots(const timet_ff_params *p);
 int timet_ff_export_selection(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int clip,
                               int t, float *weights, int32_t *keys, int32_t *counts, timet_stream_t stream);
+
+/* Copy n entries of the wide-row pool starting at `offset` (see above): weights float32 [n], keys int32 [n]. */
+int timet_ff_export_wide(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int64_t offset, int n,
+                         float *weights, int32_t *keys, timet_stream_t stream);
 
 /* Test hook of the tensor-core engine: run ONE query tile (tile_id in the kernel's launch order) after
  * timet_ff_prepare and dump its raw fp32 TMEM accumulators, float32 [n_key_tiles, 128, 256]. */

@@ -49,3 +49,21 @@ def assert_close(actual, expected, atol=ATOL, rtol=RTOL, what=""):
     bad = err > atol + rtol * np.abs(expected)
     assert not bad.any(), (f"{what}: {bad.sum()} / {bad.size} outside tol, max abs err {err.max():.3e} "
                            f"at {np.unravel_index(err.argmax(), err.shape)}")
+
+
+@pytest.fixture
+def timet_env(monkeypatch):
+    """Set TIMET_* experiment switches for one test: the library reads the environment once, so it is told to
+    re-read after every change and once more when the test is over."""
+    from timetuning_b200 import _cabi
+
+    def set_env(**kv):
+        for k, v in kv.items():
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, str(v))
+        _cabi.reload_env()
+    yield set_env
+    monkeypatch.undo()
+    _cabi.reload_env()

@@ -356,15 +356,15 @@ def test_non_square_grid_through_the_c_abi():
             assert np.abs(got[t] - segs[t]).max() < 1e-5, (engine, t)
 
 
-def test_sinkhorn_streaming_path_matches_resident(monkeypatch):
+def test_sinkhorn_streaming_path_matches_resident(timet_env):
     """The multi-launch streaming kernels (multi-GPU NCCL fallback / shapes that do not fit shared memory) against
     the resident cooperative kernel and the oracle."""
     scores = synth.cosine_scores(4 * 784, 200, seed=91)
     q_res = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
-    monkeypatch.setenv("TIMET_SK_STREAMING", "1")
+    timet_env(TIMET_SK_STREAMING="1")
     q_str = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
     q_str2 = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
-    monkeypatch.delenv("TIMET_SK_STREAMING")
+    timet_env(TIMET_SK_STREAMING=None)
     assert torch.equal(q_str, q_str2), "streaming path must be bit-reproducible"
     ref = O.sinkhorn_scaling(scores, 0.05, 10, dtype=np.float64)
     assert_close(q_str.cpu().numpy(), ref, what="streaming vs fp64 oracle")

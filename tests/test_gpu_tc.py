@@ -138,7 +138,7 @@ def test_tc_random_features_worst_case():
     {"TIMET_TC_PFLAGS": "128"},                 # every TMEM buffer scanned by its own two groups
     {"TIMET_TC_PFLAGS": "72"},                  # oldest-first contexts, threshold picked up per tile
 ], ids=lambda e: "+".join(f"{k[9:]}={v}" for k, v in e.items()))
-def test_tc_kernel_variants_are_bit_identical(monkeypatch, env):
+def test_tc_kernel_variants_are_bit_identical(timet_env, env):
     """Every kernel variant / schedule behind the experiment switches nominates a superset of the exact
     top-k, so after the fp32 re-evaluation all of them reproduce the exact engine bit for bit."""
     bs, fs, sr, D = 3, 8, 28, 384
@@ -147,11 +147,27 @@ def test_tc_kernel_variants_are_bit_identical(monkeypatch, env):
     plan.prepare(feats)
     plan.select(tb.FF_EXACT)
     ref = {(c, t): [x.clone() for x in plan.selection(c, t)] for c in range(bs) for t in range(1, fs)}
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    timet_env(**env)
     plan.select(tb.FF_TC)
     st = plan.stats()
     for (c, t), (w, k, n) in ref.items():
         w2, k2, n2 = plan.selection(c, t)
         assert torch.equal(n, n2) and torch.equal(k, k2) and torch.equal(w, w2), (env, c, t)
     assert st["redone_queries"] <= 0.02 * st["queries"], st
+
+
+def test_tc_engine_wide_features_dim_2048():
+    """ResNet-width features (dim 1537..2048): the finalize kernel needs more than 48 KB of dynamic shared memory;
+    FF_AUTO must pick the tensor-core engine and agree with the exact engine bit for bit."""
+    bs, fs, sr, D = 1, 3, 14, 2048
+    feats = torch.from_numpy(synth.clip_features(bs, fs, sr, D, seed=11)).cuda()
+    plan = tb.FFPlan(bs, fs, sr, sr, D, 8, 7, 6, 5)
+    assert plan.tc_supported
+    plan.prepare(feats)
+    plan.select(tb.FF_EXACT)
+    ref = {t: [x.clone() for x in plan.selection(0, t)] for t in range(1, fs)}
+    plan.select(tb.FF_AUTO)
+    assert plan.stats()["tc_candidates"] > 0
+    for t, (w, k, n) in ref.items():
+        w2, k2, n2 = plan.selection(0, t)
+        assert torch.equal(n, n2) and torch.equal(k, k2) and torch.equal(w, w2), t

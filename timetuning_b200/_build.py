@@ -22,7 +22,7 @@ STAMP = os.path.join(LIBDIR, "build.stamp")
 SOURCES = ["common.cu", "sinkhorn.cu", "comm.cu", "misc.cu", "ff_prepare.cu", "ff_select_exact.cu",
            "ff_gather.cu", "ff_tc.cu", "ff_tc2.cu", "ff_tc3.cu", "scores.cu", "ff_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-diag-suppress", "128"]
 
 
 def _nvcc():
@@ -49,9 +49,24 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link under an exclusive file lock: under torchrun every rank may get here at once; the first
+    one builds, the others wait and then find the library current.  The .so is linked to a temporary name and
+    renamed into place, so a concurrent loader never sees a half-written file."""
     if not force and is_current():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(LIBDIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():          # another process built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -71,12 +86,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(f"--- {src}\n{out}", file=sys.stderr)
     if failed:
         raise RuntimeError("nvcc failed:\n" + "\n".join(failed))
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
-    with open(STAMP, "w") as f:
+    os.replace(tmp, LIB)
+    with open(STAMP + ".tmp", "w") as f:
         f.write(source_hash())
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 

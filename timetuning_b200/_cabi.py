@@ -27,6 +27,7 @@ _PROTOS = {
     "timet_last_error": (C.c_char_p, []),
     "timet_abi_version": (C.c_int, []),
     "timet_launch_count": (C.c_int64, []),
+    "timet_debug_reload_env": (C.c_int, []),
     "timet_sinkhorn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "timet_sinkhorn": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "timet_cosine_scores_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
@@ -41,6 +42,7 @@ _PROTOS = {
     "timet_ff_stats": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, _P, _P]),
     "timet_ff_slots": (C.c_int, [C.POINTER(FFParams)]),
     "timet_ff_export_selection": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "timet_ff_export_wide": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, C.c_int64, C.c_int, _P, _P, _P]),
     "timet_debug_tc_tile": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, C.c_int64, _P, _P]),
     "timet_debug_tc_trace": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, _P, C.c_int, _P]),
     "timet_restrict_neighborhood": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P]),
@@ -84,6 +86,11 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = lib().timet_last_error().decode(errors="replace")
         raise RuntimeError(f"libtimet_b200 {what} failed ({rc}): {msg}")
+
+
+def reload_env() -> None:
+    """Re-read the TIMET_* experiment switches (the library reads the environment once, at first use)."""
+    lib().timet_debug_reload_env()
 
 
 def launch_count() -> int:

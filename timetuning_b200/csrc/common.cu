@@ -1,5 +1,6 @@
 // Error state, launch counter, parameter validation, ABI info.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -27,6 +28,38 @@ int num_sms() {
     return sms;
 }
 
+static EnvCfg g_env;
+static bool g_env_loaded = false;
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+void env_reload() {
+    EnvCfg e;
+    e.tc_pflags = env_int("TIMET_TC_PFLAGS", 0);
+    e.tc_flags = env_int("TIMET_TC_FLAGS", 0);
+    e.tc_stages = env_int("TIMET_TC_STAGES", 0);
+    e.tc_nbuf = env_int("TIMET_TC_NBUF", 0);
+    e.tc_clip_group = env_int("TIMET_TC_CLIP_GROUP", 0);
+    e.tc_pair = env_int("TIMET_TC_PAIR", 0) == 1;
+    e.tc_persist = env_int("TIMET_TC_PERSIST", 1) != 0;
+    e.tc_dyn = env_int("TIMET_TC_DYN", 1) != 0;
+    e.tc_trace = env_int("TIMET_TC_TRACE", 0) == 1;
+    e.sk_streaming = env_int("TIMET_SK_STREAMING", 0) == 1;
+    e.sk_ustride = env_int("TIMET_SK_USTRIDE", 0);
+    const char *to = getenv("TIMET_P2P_TIMEOUT_S");
+    e.p2p_timeout_s = (to && atof(to) > 0.0) ? atof(to) : 600.0;    // NCCL-like patience: rank skew of minutes is legal
+    g_env = e;
+    g_env_loaded = true;
+}
+
+const EnvCfg &env_cfg() {
+    if (!g_env_loaded) env_reload();
+    return g_env;
+}
+
 int ff_validate(const timet_ff_params *p) {
     TIMET_CHECK_ARG(p != nullptr, "ff: params is NULL");
     TIMET_CHECK_ARG(p->n_clips >= 1, "ff: n_clips=%d must be >= 1", p->n_clips);
@@ -52,5 +85,6 @@ extern "C" {
 const char *timet_last_error(void) { return timet::g_error; }
 int timet_abi_version(void) { return TIMET_ABI_VERSION; }
 int64_t timet_launch_count(void) { return timet::g_launches; }
+int timet_debug_reload_env(void) { timet::env_reload(); return TIMET_OK; }
 
 }

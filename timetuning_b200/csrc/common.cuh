@@ -44,6 +44,18 @@ int64_t &launch_counter();
 
 int num_sms();
 
+// Experiment / debug switches, read from the environment ONCE (first use) -- never on the launch path.
+// timet_debug_reload_env() re-reads them (tests flip switches inside one process).
+struct EnvCfg {
+    int tc_pflags, tc_flags, tc_stages, tc_nbuf, tc_clip_group;   // 0 = default
+    bool tc_pair, tc_persist, tc_dyn, tc_trace;
+    bool sk_streaming;
+    int sk_ustride;                                                // 0 = default
+    double p2p_timeout_s;                                          // peer-exchange / marginal wait time-out (seconds)
+};
+const EnvCfg &env_cfg();
+void env_reload();
+
 // ------------------------------------------------------------------ peer-memory exchange buffer (one per rank)
 constexpr int P2P_MAX_RANKS = 16;
 constexpr int P2P_MAX_K = 1024;
@@ -59,12 +71,18 @@ constexpr int FF_CAND_CAP = 32;     // in-kernel candidate list capacity per (qu
 constexpr int FF_CAND_STORE = 16;   // candidates published per query after the merged final compaction
 constexpr int FF_TRACE_CTAS = 4096;  // debug timeline (env TIMET_TC_TRACE): first CTAs x 8 globaltimer stamps
 constexpr int FF_TRACE_SLOTS = 8;
+// header of the redo region (256 bytes, zeroed by timet_ff_select): byte offsets of its counters
+constexpr int FF_HDR_REDO_COUNT = 0;     // u32: queries queued for the exact re-do
+constexpr int FF_HDR_NEXT_ITEM = 128;    // u32: work counter of the persistent tensor-core kernel
+constexpr int FF_HDR_WIDE_USED = 192;    // u64: entries allocated in the wide-row pool
 
 struct FFLayout {
     int N, Dp, nT, kw;               // patches, padded dim (multiple of 64), target frames, slots per query
     int64_t rows;                    // n_clips * n_frames * N feature rows
     int64_t queries;                 // n_clips * nT * N
     size_t off_fn32, off_fn16, off_sel_w, off_sel_k, off_sel_cnt, off_cand, off_cand_meta, off_stats, off_redo, off_trace;
+    size_t off_wide_w, off_wide_k;   // overflow pool for rows with more than kw kept entries (exact tie sets)
+    int64_t wide_cap;                // pool capacity in entries
     size_t total;
 };
 
@@ -90,6 +108,11 @@ static inline FFLayout ff_layout(const timet_ff_params &p) {
     L.off_stats = o; o = align_up(o + 8 * sizeof(int64_t), 1024);
     L.off_redo = o; o = align_up(o + 256 + (size_t)L.queries * sizeof(int32_t), 1024);   // count header + query ids
     L.off_trace = o; o = align_up(o + (size_t)FF_TRACE_CTAS * FF_TRACE_SLOTS * sizeof(unsigned long long), 1024);
+    // wide rows: the reference keeps EVERY key tied with the k-th affinity (mask_propagation.py:432-436); rows with more
+    // than kw survivors go to this pool (variable length, allocated with one atomic per row)
+    L.wide_cap = L.queries * 4 < 65536 ? 65536 : (L.queries * 4 > (int64_t)(1 << 24) ? (int64_t)(1 << 24) : L.queries * 4);
+    L.off_wide_w = o; o = align_up(o + (size_t)L.wide_cap * sizeof(float), 1024);
+    L.off_wide_k = o; o = align_up(o + (size_t)L.wide_cap * sizeof(int32_t), 1024);
     L.total = o;
     return L;
 }

@@ -130,6 +130,21 @@ int timet_ff_export_selection(const timet_ff_params *p, const void *workspace, s
 }
 
 
+int timet_ff_export_wide(const timet_ff_params *p, const void *workspace, size_t workspace_bytes, int64_t offset, int n,
+                         float *weights, int32_t *keys, timet_stream_t stream) {
+    FFLayout L;
+    int rc = check_ws(p, workspace, workspace_bytes, &L);
+    if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(weights && keys, "ff_export_wide: NULL output");
+    TIMET_CHECK_ARG(offset >= 0 && n >= 0 && offset + n <= L.wide_cap, "ff_export_wide: [%lld, +%d) outside the pool of %lld entries",
+                    (long long)offset, n, (long long)L.wide_cap);
+    const char *ws = (const char *)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    TIMET_CUDA(cudaMemcpyAsync(weights, ws + L.off_wide_w + (size_t)offset * sizeof(float), (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TIMET_CUDA(cudaMemcpyAsync(keys, ws + L.off_wide_k + (size_t)offset * sizeof(int32_t), (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return TIMET_OK;
+}
+
 int timet_debug_tc_tile(const timet_ff_params *p, void *workspace, size_t workspace_bytes, int64_t tile_id, float *dump,
                         timet_stream_t stream) {
     FFLayout L;

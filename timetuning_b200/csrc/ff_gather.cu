@@ -51,8 +51,9 @@ __device__ __forceinline__ void ga_fma(float4 &a, float w, const float4 l) {
 template <typename V, bool CLUSTER>
 __global__ void __launch_bounds__(GA_THREADS, 2)
 ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const float *__restrict__ sel_w,
-                 const int32_t *__restrict__ sel_k, const int32_t *__restrict__ sel_cnt, int n_frames, int N, int C,
-                 int nT, int kw, int t_begin, int t_first, int t_last, int vcs) {
+                 const int32_t *__restrict__ sel_k, const int32_t *__restrict__ sel_cnt, const float *__restrict__ wide_w,
+                 const int32_t *__restrict__ wide_k, int n_frames, int N, int C, int nT, int kw, int t_begin, int t_first,
+                 int t_last, int vcs) {
     const unsigned cs = CLUSTER ? cluster_nctarank() : (unsigned)vcs;
     const unsigned cr = CLUSTER ? cluster_ctarank() : (blockIdx.x % (unsigned)vcs);
     const int clip = blockIdx.x / cs;
@@ -81,26 +82,39 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
                 if (lane < kw) { w_n = __ldg(sel_w + (q0 + inext) * kw + lane); k_n = __ldg(sel_k + (q0 + inext) * kw + lane); }
             }
             V *dst = reinterpret_cast<V *>(clip_base + ((int64_t)t * N + i) * C);
+            // cnt < 0: wide row (more than kw survivors: exact tie sets) of -cnt entries in the pool at offset sel_k[0]
+            const int n_row = cnt < 0 ? -cnt : cnt;
+            const int wide_off = cnt < 0 ? __shfl_sync(0xffffffffu, k_l, 0) : 0;
             for (int c0 = 0; c0 < CV; c0 += 64) {          // warp-uniform: the shuffles below need every lane
                 const int c = c0 + lane, c2 = c + 32;
                 const bool one = c < CV, two = c2 < CV;
                 V acc0 = ga_zero<V>(), acc1 = ga_zero<V>();
-                for (int m0 = 0; m0 < cnt; m0 += 4) {
-                    float wm[4];
-                    V l0[4], l1[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int m = min(m0 + u, 31);
-                        wm[u] = __shfl_sync(0xffffffffu, w_l, m);
-                        const int32_t km = __shfl_sync(0xffffffffu, k_l, m);
-                        const V *row = reinterpret_cast<const V *>(clip_base + (int64_t)km * C);
-                        const bool on = m0 + u < cnt;
-                        l0[u] = (on && one) ? __ldcg(row + c) : ga_zero<V>();
-                        l1[u] = (on && two) ? __ldcg(row + c2) : ga_zero<V>();
+                for (int base = 0; base < n_row; base += 32) {
+                    float w_c = w_l;
+                    int32_t k_c = k_l;
+                    if (cnt < 0) {
+                        const bool in = base + lane < n_row;
+                        w_c = in ? __ldg(wide_w + wide_off + base + lane) : 0.f;
+                        k_c = in ? __ldg(wide_k + wide_off + base + lane) : 0;
                     }
+                    const int n_c = min(32, n_row - base);
+                    for (int m0 = 0; m0 < n_c; m0 += 4) {
+                        float wm[4];
+                        V l0[4], l1[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (m0 + u < cnt) { ga_fma(acc0, wm[u], l0[u]); ga_fma(acc1, wm[u], l1[u]); }
+                        for (int u = 0; u < 4; ++u) {
+                            const int m = min(m0 + u, 31);
+                            wm[u] = __shfl_sync(0xffffffffu, w_c, m);
+                            const int32_t km = __shfl_sync(0xffffffffu, k_c, m);
+                            const V *row = reinterpret_cast<const V *>(clip_base + (int64_t)km * C);
+                            const bool on = m0 + u < n_c;
+                            l0[u] = (on && one) ? __ldcg(row + c) : ga_zero<V>();
+                            l1[u] = (on && two) ? __ldcg(row + c2) : ga_zero<V>();
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (m0 + u < n_c) { ga_fma(acc0, wm[u], l0[u]); ga_fma(acc1, wm[u], l1[u]); }
+                        }
                     }
                 }
                 if (one) dst[c] = acc0;
@@ -111,6 +125,8 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
         if (CLUSTER) cluster_barrier();
     }
     if (hard && t_last == n_frames - 1) {   // argmax over channels of the last frame, lowest index on ties (time_tuning.py:296)
+        // the rows read below were stored by other lanes of this warp (float4 stores, scalar loads): order them
+        if (!CLUSTER) { __threadfence_block(); __syncwarp(); }
         for (int i = wid; i < N; i += nw) {
             const float *row = clip_base + ((int64_t)(n_frames - 1) * N + i) * C;
             float best = -INFINITY;
@@ -134,6 +150,8 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
     const float *sel_w = reinterpret_cast<const float *>(ws + L.off_sel_w);
     const int32_t *sel_k = reinterpret_cast<const int32_t *>(ws + L.off_sel_k);
     const int32_t *sel_cnt = reinterpret_cast<const int32_t *>(ws + L.off_sel_cnt);
+    const float *wide_w = reinterpret_cast<const float *>(ws + L.off_wide_w);
+    const int32_t *wide_k = reinterpret_cast<const int32_t *>(ws + L.off_wide_k);
     const bool vec = (p.n_channels % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0);
     const int nfr = p.n_frames, nch = p.n_channels, tb = p.t_begin;
     if ((int64_t)p.n_clips * 8 >= num_sms() / 2) {
@@ -153,10 +171,10 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         if (vec)
-            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4, true>, labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4, true>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                           L.nT, L.kw, tb, tb, nfr - 1, cs));
         else
-            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float, true>, labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float, true>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                           L.nT, L.kw, tb, tb, nfr - 1, cs));
         TIMET_LAUNCHED();
         return TIMET_OK;
@@ -168,10 +186,10 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
     if (vcs < 1) vcs = 1;
     for (int t = tb; t < nfr; ++t) {
         if (vec)
-            ff_gather_kernel<float4, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+            ff_gather_kernel<float4, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                                                                   L.nT, L.kw, tb, t, t, vcs);
         else
-            ff_gather_kernel<float, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, nfr, L.N, nch,
+            ff_gather_kernel<float, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                                                                  L.nT, L.kw, tb, t, t, vcs);
         TIMET_LAUNCHED();
     }

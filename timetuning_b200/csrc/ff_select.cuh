@@ -39,6 +39,12 @@ __device__ __forceinline__ void list_offer(TopList &L, bool valid, float aff, in
     }
 }
 
+// Number of list entries that survive the reference's selection (everything >= the k-th value).  Warp-uniform.
+__device__ __forceinline__ int list_kept(const TopList &L, int k, int lane) {
+    const bool keep = lane < L.cnt && (L.cnt < k || L.v >= L.kth);
+    return __popc(__ballot_sync(0xffffffffu, keep));
+}
+
 // Normalise the survivors and write the sparse row.  Returns the number of kept entries
 // (before truncation to kw).
 __device__ __forceinline__ int list_finish(const TopList &L, int k, int kw, int lane, float *__restrict__ w_out,

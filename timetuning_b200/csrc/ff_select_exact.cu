@@ -14,11 +14,77 @@ namespace timet {
 
 constexpr int EX_WARPS = 8;
 
+struct WidePool {
+    float *w;              // [cap] normalised weights
+    int32_t *k;            // [cap] keys (frame * N + patch)
+    unsigned long long *used;   // entries allocated so far (zeroed by timet_ff_select); 64-bit: never wraps
+    unsigned long long cap;
+};
+
+// Second scan of one query whose survivor set does not fit kw slots: every in-window key with aff >= theta is kept,
+// exactly like the reference (mask_propagation.py:434-436: aff[aff < kth] = 0; aff /= aff.sum()).  Two passes over the
+// window (count + sum, then emit in scan order = context-major, window row-major: deterministic); the row lives in the
+// pool, its descriptor in the regular slots: sel_cnt = -n, sel_k[0] = pool offset.  Returns false if the pool is full.
+__device__ __forceinline__ bool ex_wide_row(const timet_ff_params &p, int N, int Dp, const float *__restrict__ fn32,
+                                            const float4 *qs, int64_t clip_row0, int t, int r0, int c0, int wcols, int nwin,
+                                            float theta, int lane, const WidePool &pool, float *__restrict__ w_out,
+                                            int32_t *__restrict__ k_out, int32_t *__restrict__ cnt_out, int kw, int *n_out) {
+    const int W = p.grid_w;
+    const int nctx = ctx_count(t, p.n_last_frames);
+    unsigned long long off = 0;
+    float total = 0.f;
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        float part = 0.f;
+        int emitted = 0;
+        for (int ci = 0; ci < nctx; ++ci) {
+            const int f = ctx_frame(t, p.n_last_frames, ci);
+            const float *fbase = fn32 + (clip_row0 + (int64_t)f * N) * Dp;
+            for (int m0 = 0; m0 < nwin; m0 += 32) {
+                const int m = m0 + lane;
+                float aff = -1.f;
+                int32_t key = 0;
+                if (m < nwin) {
+                    const int wr = m / wcols;
+                    const int j = (r0 + wr) * W + c0 + (m - wr * wcols);
+                    const float sim = dot_canonical_seq(qs, reinterpret_cast<const float4 *>(fbase + (int64_t)j * Dp), Dp >> 2);
+                    aff = affinity_from_sim(sim, p.temperature);
+                    key = f * N + j;
+                }
+                const bool hit = aff >= theta;
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (pass == 0) {
+                    if (hit) part += aff;
+                } else if (hit) {
+                    const unsigned long long slot = off + (unsigned)emitted + (unsigned)__popc(mask & ((1u << lane) - 1u));
+                    pool.w[slot] = __fdiv_rn(aff, total);
+                    pool.k[slot] = key;
+                }
+                emitted += __popc(mask);
+            }
+        }
+        if (pass == 0) {
+            n = emitted;
+            total = warp_sum(part);
+            if (lane == 0) off = atomicAdd(pool.used, (unsigned long long)n);
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (off + (unsigned long long)n > pool.cap) return false;
+        }
+    }
+    if (lane < kw) {
+        w_out[lane] = 0.f;
+        k_out[lane] = (lane == 0) ? (int32_t)off : -1;
+    }
+    if (lane == 0) *cnt_out = -n;
+    *n_out = n;
+    return true;
+}
+
 __global__ void __launch_bounds__(EX_WARPS * 32)
 ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float *__restrict__ fn32,
                        float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
                        unsigned long long *__restrict__ stats, const int32_t *__restrict__ qlist,
-                       const unsigned int *__restrict__ qcount, int64_t n_queries) {
+                       const unsigned int *__restrict__ qcount, int64_t n_queries, WidePool pool) {
     extern __shared__ float4 qsm[];                       // [EX_WARPS][Dp/4]
     __shared__ unsigned long long s_stat[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -28,7 +94,7 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
     const int H = p.grid_h, W = p.grid_w;
     const int64_t total = qlist ? (int64_t)*qcount : n_queries;
     const int64_t nwarps = (int64_t)gridDim.x * EX_WARPS;
-    unsigned long long st_sel = 0, st_ties = 0, st_trunc = 0;
+    unsigned long long st_sel = 0, st_ties = 0, st_trunc = 0, st_wide = 0;
 
     for (int64_t it = (int64_t)blockIdx.x * EX_WARPS + warp; it < total; it += nwarps) {
         const int64_t qid = qlist ? (int64_t)qlist[it] : it;
@@ -72,22 +138,37 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
                 list_offer(L, valid, aff, key, p.topk, lane);
             }
         }
-        const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);
-        st_sel += (unsigned long long)(m < kw ? m : kw);
+        // survivors: everything >= the k-th value.  The sorted list holds the 32 largest entries, so the k-th value is
+        // exact; the survivor SET is complete unless it fills all kw slots' worth (or all 32 list slots with entries
+        // dropped behind them) -- then the query is rescanned into a variable-length row of the pool.
+        const int m_list = list_kept(L, p.topk, lane);
+        int m = m_list;
+        bool done = false;
+        if (m_list > kw || (m_list == 32 && L.dropped > 0)) {
+            int n_wide = 0;
+            done = ex_wide_row(p, N, Dp, fn32, qs, clip_row0, t, r0, c0, wcols, nwin, L.kth, lane, pool, sel_w + qid * kw,
+                               sel_k + qid * kw, sel_cnt + qid, kw, &n_wide);
+            if (done) { m = n_wide; st_wide += 1; st_sel += (unsigned long long)n_wide; }
+            else st_trunc += 1;                     // pool exhausted: the row below is truncated to kw entries
+        }
+        if (!done) {
+            list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);
+            st_sel += (unsigned long long)(m < kw ? m : kw);
+        }
         st_ties += (m > p.topk);
-        st_trunc += (m > kw || L.dropped > 0);
     }
     if (lane == 0) {
         atomicAdd(&s_stat[0], st_sel);
         atomicAdd(&s_stat[1], st_ties);
         atomicAdd(&s_stat[2], st_trunc);
+        atomicAdd(&s_stat[3], st_wide);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (!qlist) atomicAdd(&stats[0], (unsigned long long)0);   // queries counted by the host
         if (s_stat[0]) atomicAdd(&stats[1], s_stat[0]);
         if (s_stat[1]) atomicAdd(&stats[2], s_stat[1]);
         if (s_stat[2]) atomicAdd(&stats[5], s_stat[2]);
+        if (s_stat[3]) atomicAdd(&stats[6], s_stat[3]);
     }
 }
 
@@ -101,11 +182,16 @@ int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, c
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    WidePool pool;
+    pool.w = reinterpret_cast<float *>(ws + L.off_wide_w);
+    pool.k = reinterpret_cast<int32_t *>(ws + L.off_wide_k);
+    pool.used = reinterpret_cast<unsigned long long *>(ws + L.off_redo + FF_HDR_WIDE_USED);
+    pool.cap = (unsigned long long)L.wide_cap;
     ff_select_exact_kernel<<<(int)blocks, EX_WARPS * 32, smem, st>>>(
         p, L.N, L.Dp, L.nT, L.kw, reinterpret_cast<const float *>(ws + L.off_fn32),
         reinterpret_cast<float *>(ws + L.off_sel_w), reinterpret_cast<int32_t *>(ws + L.off_sel_k),
         reinterpret_cast<int32_t *>(ws + L.off_sel_cnt), reinterpret_cast<unsigned long long *>(ws + L.off_stats),
-        qlist, qcount, L.queries);
+        qlist, qcount, L.queries, pool);
     TIMET_LAUNCHED();
     return TIMET_OK;
 }

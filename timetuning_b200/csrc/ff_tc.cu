@@ -482,10 +482,10 @@ bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
     // 4 accumulator buffers of 128 TMEM columns (one epilogue group each) or 2 x 256 (two groups per buffer,
     // splitting the key rows).  Bigger key tiles amortise the per-tile pipeline overhead better, so 2 x 256 is the
     // default; TIMET_TC_NBUF=4 selects the other layout for experiments.
-    const char *nb = getenv("TIMET_TC_NBUF");
+    const EnvCfg &E = env_cfg();
     int RPC = (256 / W) / qrows * qrows;
     G->nbuf = 2;
-    if (nb && atoi(nb) == 4 && (128 / W) / qrows >= 1) { RPC = (128 / W) / qrows * qrows; G->nbuf = 4; }
+    if (E.tc_nbuf == 4 && (128 / W) / qrows >= 1) { RPC = (128 / W) / qrows * qrows; G->nbuf = 4; }
     G->buf_cols = 512 / G->nbuf;
     G->H = H; G->W = W; G->N = L.N; G->Dp = L.Dp; G->NKC = L.Dp / 64;
     G->QR = (128 / W) < H ? (128 / W) : H;
@@ -493,14 +493,11 @@ bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
     G->RPC = RPC; G->NT = RPC * W; G->qrows = qrows;
     G->n_clips = p.n_clips; G->n_frames = p.n_frames; G->nT = L.nT; G->t_begin = p.t_begin;
     G->n_last = p.n_last_frames; G->radius = p.radius; G->topk = p.topk;
-    const char *fl = getenv("TIMET_TC_FLAGS");
-    G->flags = fl ? atoi(fl) : 0;
-    const char *cg = getenv("TIMET_TC_CLIP_GROUP");
-    G->clip_group = (cg && atoi(cg) >= 1) ? atoi(cg) : TC_CLIP_GROUP;
+    G->flags = E.tc_flags;
+    G->clip_group = E.tc_clip_group >= 1 ? E.tc_clip_group : TC_CLIP_GROUP;
     G->total_tiles = (int64_t)p.n_clips * L.nT * G->tiles_per_frame;
     G->nstages = TC_MAX_STAGES;                                  // as deep a B ring as shared memory allows
-    const char *ns = getenv("TIMET_TC_STAGES");
-    if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G->nstages = atoi(ns);
+    if (E.tc_stages >= 2 && E.tc_stages <= TC_MAX_STAGES) G->nstages = E.tc_stages;
     while (tc_smem_bytes(*G) > 227 * 1024 && G->nstages > 2) G->nstages--;
     return tc_smem_bytes(*G) <= 227 * 1024;
 }
@@ -533,16 +530,13 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
     uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_cand_meta);
     if (g_ev_nominate_begin) TIMET_CUDA(cudaEventRecord(g_ev_nominate_begin, st));
     // nomination: 1-CTA kernel by default; TIMET_TC_PAIR=1 selects the CTA-pair kernel (cta_group::2, ff_tc2.cu)
-    const char *pe = getenv("TIMET_TC_PAIR");
-    rc = (pe && pe[0] == '1') ? ff_select_tc_pair_launch(p, L, ws, st) : TIMET_ERR_UNSUPPORTED;   // opt-in
+    const EnvCfg &E = env_cfg();
+    rc = E.tc_pair ? ff_select_tc_pair_launch(p, L, ws, st) : TIMET_ERR_UNSUPPORTED;   // opt-in
     if (rc != TIMET_OK && rc != TIMET_ERR_UNSUPPORTED) return rc;
     if (rc == TIMET_ERR_UNSUPPORTED) {
         // persistent kernel (ff_tc3.cu): one CTA per SM walks the work items; TIMET_TC_PERSIST=0 selects the per-tile kernel
-        const char *ps = getenv("TIMET_TC_PERSIST");
-        const char *trc = getenv("TIMET_TC_TRACE");
-        const char *flg = getenv("TIMET_TC_FLAGS");
-        const bool debug = (trc && trc[0] == '1') || (flg && atoi(flg) != 0);
-        if (!(ps && ps[0] == '0') && !debug) {
+        const bool debug = E.tc_trace || E.tc_flags != 0;
+        if (E.tc_persist && !debug) {
             rc = ff_select_tc_persist_launch(p, L, ws, st);
             if (rc != TIMET_OK && rc != TIMET_ERR_UNSUPPORTED) return rc;
         }
@@ -554,8 +548,7 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
         if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
         const size_t smem = tc_smem_bytes(G);
         TIMET_CUDA(cudaFuncSetAttribute(ff_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const char *tr = getenv("TIMET_TC_TRACE");
-        unsigned long long *trace = (tr && tr[0] == '1') ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
+        unsigned long long *trace = E.tc_trace ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
         ff_tc_kernel<false><<<(unsigned)G.total_tiles, TC_THREADS, smem, st>>>(map_a, map_b, G, cand, meta, -1, nullptr, trace);
         TIMET_LAUNCHED();
     }
@@ -564,6 +557,8 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
     unsigned int *redo_count = reinterpret_cast<unsigned int *>(ws + L.off_redo);
     int32_t *redo_list = reinterpret_cast<int32_t *>(ws + L.off_redo + 256);
     const size_t fsmem = (size_t)FIN_WARPS * L.Dp * sizeof(float);
+    if (fsmem > 48 * 1024)
+        TIMET_CUDA(cudaFuncSetAttribute(ff_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     const int64_t blocks = (L.queries + FIN_QPB - 1) / FIN_QPB;
     ff_finalize_kernel<<<(unsigned)blocks, FIN_WARPS * 32, fsmem, st>>>(
         p, L.N, L.Dp, L.nT, L.kw, reinterpret_cast<const float *>(ws + L.off_fn32), cand, meta,

@@ -373,8 +373,8 @@ int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *
     TcGeom &G = PG.g;
     if ((G.NT / 2) % 8 != 0 || !G.a_resident) return TIMET_ERR_UNSUPPORTED;
     G.nstages = TC_MAX_STAGES;
-    const char *ns = getenv("TIMET_TC_STAGES");
-    if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G.nstages = atoi(ns);
+    const EnvCfg &E = env_cfg();
+    if (E.tc_stages >= 2 && E.tc_stages <= TC_MAX_STAGES) G.nstages = E.tc_stages;
     while (pair_smem_bytes(G) > 227 * 1024 && G.nstages > 2) G.nstages--;
     if (pair_smem_bytes(G) > 227 * 1024) return TIMET_ERR_UNSUPPORTED;
     PG.pairs_per_cq = (L.nT + 1) / 2;
@@ -389,8 +389,7 @@ int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *
     TIMET_CUDA(cudaFuncSetAttribute(ff_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     uint32_t *cand = reinterpret_cast<uint32_t *>(ws + L.off_cand);
     uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_cand_meta);
-    const char *tr = getenv("TIMET_TC_TRACE");
-    unsigned long long *trace = (tr && tr[0] == '1') ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
+    unsigned long long *trace = E.tc_trace ? reinterpret_cast<unsigned long long *>(ws + L.off_trace) : nullptr;
     ff_tc_pair_kernel<<<(unsigned)(2 * PG.total_pairs), TC_THREADS, smem, st>>>(map_a, map_b, PG, cand, meta, trace);
     TIMET_LAUNCHED();
     return TIMET_OK;

@@ -384,9 +384,9 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
     TcGeom G;
     if (!tc_geometry(p, L, &G)) return TIMET_ERR_UNSUPPORTED;
     G.nstages = TC_MAX_STAGES;
-    { const char *pf = getenv("TIMET_TC_PFLAGS"); G.flags = pf ? atoi(pf) : 0; }
-    const char *ns = getenv("TIMET_TC_STAGES");
-    if (ns && atoi(ns) >= 2 && atoi(ns) <= TC_MAX_STAGES) G.nstages = atoi(ns);
+    const EnvCfg &E = env_cfg();
+    G.flags = E.tc_pflags;
+    if (E.tc_stages >= 2 && E.tc_stages <= TC_MAX_STAGES) G.nstages = E.tc_stages;
     while (persist_smem_bytes(G) > 227 * 1024 && G.nstages > 2) G.nstages--;
     if (persist_smem_bytes(G) > 227 * 1024) return TIMET_ERR_UNSUPPORTED;
     const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
@@ -395,11 +395,10 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
     if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
     if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
     const size_t smem = persist_smem_bytes(G);
-    const char *dy = getenv("TIMET_TC_DYN");
-    auto kern = (dy && dy[0] == '0') ? ff_tc_persist_kernel<false> : ff_tc_persist_kernel<true>;
+    auto kern = E.tc_dyn ? ff_tc_persist_kernel<true> : ff_tc_persist_kernel<false>;
     TIMET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = G.total_tiles < num_sms() ? G.total_tiles : num_sms();
-    unsigned int *next_item = reinterpret_cast<unsigned int *>(ws + L.off_redo + 128);   // zeroed with the redo header by timet_ff_select
+    unsigned int *next_item = reinterpret_cast<unsigned int *>(ws + L.off_redo + FF_HDR_NEXT_ITEM);   // zeroed with the redo header by timet_ff_select
     kern<<<(unsigned)grid, TC_THREADS, smem, st>>>(map_a, map_b, G, reinterpret_cast<uint32_t *>(ws + L.off_cand),
                                                                   reinterpret_cast<uint32_t *>(ws + L.off_cand_meta), next_item);
     TIMET_LAUNCHED();

@@ -265,10 +265,17 @@ struct SkResArgs {
     void *const *peers;       // world_size > 1: every rank's P2PBuf (NVLink peer memory), else nullptr
     int rank, ws;
     unsigned long long epoch0; // exchanges completed before this call (same on every rank)
+    unsigned long long timeout_ns; // patience of the in-kernel waits (env TIMET_P2P_TIMEOUT_S, default 10 min)
     int64_t B;
     int K, iters, rows_per_cta, scores_mode;
     float inv_eps, r, c;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
     __syncthreads();
@@ -327,12 +334,24 @@ __device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long l
     }
     if ((int)threadIdx.x < A.ws) {
         const unsigned long long *f = &own->flag[threadIdx.x];
-        unsigned long long v;
+        // A peer may legitimately arrive late (lazy library build, data loader stall, checkpointing): wait like a
+        // blocking NCCL collective would, by wall clock (%globaltimer), not by a spin count.
+        unsigned long long v, t0 = 0ull;
         unsigned int spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (++spins > (1u << 26)) { printf("timet: sinkhorn peer exchange timed out (rank %d waiting for rank %d, exchange %llu)\n", A.rank, (int)threadIdx.x, e); __trap(); }
-        } while (v < e + 1ull);
+            if (v >= e + 1ull) break;
+            if ((++spins & 0xFFFu) == 0u) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0ull) t0 = now;
+                else if (now - t0 > A.timeout_ns) {
+                    printf("timet: sinkhorn peer exchange timed out after %llu s (rank %d waiting for rank %d, exchange %llu)\n",
+                           A.timeout_ns / 1000000000ull, A.rank, (int)threadIdx.x, e);
+                    __trap();
+                }
+                __nanosleep(200);
+            }
+        } while (true);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
@@ -469,12 +488,21 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
             for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
             unsigned long long *acc_i = ufix + (size_t)i * A.ustride;
             atomicAdd(acc_i, ((unsigned long long)__float2ll_rn(t * A.ufix_scale) << SKR_CNT_BITS) + 1ull);
-            unsigned long long v;
+            // with world_size > 1 another CTA of this grid may itself be waiting for a late peer: same patience
+            unsigned long long v, t0 = 0ull;
             unsigned int spins = 0;
             do {
                 asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(acc_i) : "memory");
-                if (++spins > (1u << 24)) { printf("timet: sinkhorn marginal wait timed out (block %d column %d iteration %d)\n", (int)blockIdx.x, i, it); __trap(); }
-            } while ((v & ((1ull << SKR_CNT_BITS) - 1ull)) < want);
+                if ((v & ((1ull << SKR_CNT_BITS) - 1ull)) >= want) break;
+                if ((++spins & 0xFFFFu) == 0u) {
+                    const unsigned long long now = globaltimer_ns();
+                    if (t0 == 0ull) t0 = now;
+                    else if (now - t0 > A.timeout_ns) {
+                        printf("timet: sinkhorn marginal wait timed out (block %d column %d iteration %d)\n", (int)blockIdx.x, i, it);
+                        __trap();
+                    }
+                }
+            } while (true);
             const unsigned long long cur = v >> SKR_CNT_BITS;
             const unsigned long long prev = (it & 1) ? prev1 : prev0;
             u_mine = (float)((double)(long long)(cur - prev) * (double)A.ufix_inv);            // local u_i
@@ -575,12 +603,12 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
     {   // single GPU, >= 1 iteration, rows fit in shared memory: one cooperative launch
         int rgrid, rpc;
         size_t rsmem;
-        const char *force = getenv("TIMET_SK_STREAMING");
+        const EnvCfg &E = env_cfg();
         void **peers = nullptr;
         int prank = 0, pws = 1;
         unsigned long long *pepoch = nullptr;
         const bool p2p = world_size > 1 && comm_p2p_info(comm, &peers, &prank, &pws, &pepoch) && pws == world_size && K <= P2P_MAX_K;
-        if ((world_size == 1 || p2p) && iters >= 1 && !(force && force[0] == '1') && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+        if ((world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
             (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160 &&
             (int64_t)(iters / 2 + 1) * rgrid < (1 << SKR_CNT_BITS)) {      // arrival counts of a call fit their 16 bits
             float *partials = (float *)workspace;
@@ -588,8 +616,7 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
             // bar (64 B slot) followed by the 8-byte aligned fixed-point buffers; one memset clears both
             const size_t bar_off = (size_t)322 * K * sizeof(float);
             const size_t ufix_off = align_up(bar_off + 64, 256);
-            const char *us = getenv("TIMET_SK_USTRIDE");        // 1 = packed accumulators (for comparison)
-            const int ustride = (us && atoi(us) >= 1 && atoi(us) <= SKR_USTRIDE) ? atoi(us) : SKR_USTRIDE;
+            const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;   // 1 = packed accumulators (for comparison)
             TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
             SkResArgs R;
             R.ustride = ustride;
@@ -605,6 +632,7 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
             R.r = 1.0f / (float)K; R.c = 1.0f / ((float)B * (float)world_size);
             R.peers = p2p ? peers : nullptr; R.rank = prank; R.ws = p2p ? pws : 1;
             R.epoch0 = p2p ? *pepoch : 0ull;
+            R.timeout_ns = (unsigned long long)(E.p2p_timeout_s * 1e9);
             if (p2p) *pepoch += (unsigned long long)iters;             // pass 0 + (iters - 1) iterations exchange a vector
             switch ((K / 4 + 31) / 32) {
                 case 1: return sk_resident_launch<1>(R, rgrid, rsmem, st);

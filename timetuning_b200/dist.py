@@ -73,10 +73,16 @@ def init_comm(p2p: bool = True):
         if int(flag.item()) == 0:
             _cabi.check(lib.timet_comm_p2p_disable(handle), "comm_p2p_disable")
         ops._comm["p2p"] = bool(int(flag.item()))
+    else:
+        ops._comm["p2p"] = False
+    # Every rank has loaded (or built) the library and mapped its peers by now; make that a synchronisation point so
+    # that the first in-kernel peer exchange does not start minutes apart on different ranks.  (The in-kernel waits are
+    # wall-clock bounded anyway: env TIMET_P2P_TIMEOUT_S, default 600 s.)
+    dist.barrier()
     return handle
 
 
 def destroy_comm():
     if ops._comm["handle"] is not None:
         _cabi.check(_cabi.lib().timet_comm_destroy(ops._comm["handle"]), "comm_destroy")
-        ops._comm.update(handle=None, world_size=1, rank=0)
+        ops._comm.update(handle=None, world_size=1, rank=0, p2p=False)

@@ -23,7 +23,7 @@ from . import _cabi
 from ._cabi import FFParams, FF_AUTO, FF_EXACT, FF_TC, SK_EXP, SK_SCORES, check
 
 AFF_TEMPERATURE = 0.1          # mask_propagation.py:422
-_comm = {"handle": None, "world_size": 1, "rank": 0}
+_comm = {"handle": None, "world_size": 1, "rank": 0, "p2p": False}
 
 
 # --------------------------------------------------------------------------- plumbing
@@ -257,10 +257,28 @@ class FFPlan:
                                              _stream()), "ff_stats")
         v = out.tolist()
         return dict(queries=v[0], selected=v[1], tie_queries=v[2], tc_candidates=v[3], redone_queries=v[4],
-                    truncated_queries=v[5])
+                    truncated_queries=v[5], wide_rows=v[6])
+
+    def check_complete(self):
+        """Raise if the last select() had to truncate a tie set (wide-row pool exhausted): the result would differ
+        from the reference, which keeps every key tied with the k-th affinity (mask_propagation.py:432-436)."""
+        n = self.stats()["truncated_queries"]
+        if n:
+            raise RuntimeError(f"Feature-Forwarding: {n} queries have more exact affinity ties than the wide-row pool holds "
+                               "(degenerate features, e.g. constant rows); the result would not match the reference")
+
+    def wide_row(self, offset, n):
+        """(weights [n], keys [n]) of a wide row (counts[i] = -n, keys[i, 0] = offset in `selection`)."""
+        w = torch.empty((n,), dtype=torch.float32, device=self.device)
+        k = torch.empty((n,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().timet_ff_export_wide(C.byref(self.params), _ptr(self.workspace), self.nbytes, int(offset), int(n),
+                                                   _ptr(w), _ptr(k), _stream()), "ff_export_wide")
+        return w, k
 
     def selection(self, clip, t):
-        """(weights [N, kw] fp32, keys [N, kw] int32 = frame*N+patch or -1, counts [N] int32)."""
+        """(weights [N, kw] fp32, keys [N, kw] int32 = frame*N+patch or -1, counts [N] int32; counts[i] = -n marks a
+        wide row of n > kw entries whose pool offset is keys[i, 0], see wide_row)."""
         w = torch.empty((self.N, self.kw), dtype=torch.float32, device=self.device)
         k = torch.empty((self.N, self.kw), dtype=torch.int32, device=self.device)
         c = torch.empty((self.N,), dtype=torch.int32, device=self.device)
@@ -286,7 +304,7 @@ def _plan(*key, device):
 
 @torch.no_grad()
 def propagate_labels_batched(feats, first_labels, n_last_frames=7, size_mask_neighborhood=6, topk=5,
-                             engine=FF_AUTO, want_hard=True):
+                             engine=FF_AUTO, want_hard=True, check=False):
     """Additive fast entry: every clip of a batch in one call (replaces the per-clip Python loop of
     TimeT.get_loss, time_tuning.py:277-296).
 
@@ -305,6 +323,8 @@ def propagate_labels_batched(feats, first_labels, n_last_frames=7, size_mask_nei
     labels[:, 0] = first_labels.reshape(bs, N, Cc)
     hard = torch.empty((bs, N), dtype=torch.int64, device=feats.device) if want_hard else None
     plan.propagate(feats, labels, hard, engine)
+    if check:               # one small device->host read: only the drop-in shims pay for it by default
+        plan.check_complete()
     return labels, (hard.view(bs, sr, sr) if want_hard else None)
 
 
@@ -330,7 +350,7 @@ def propagate_labels(n_last_frames, size_mask_neighborhood, topk, model, frame_l
     Cc = seg.shape[1]
     first = seg[0].reshape(Cc, N).t().float()                                            # channel-last [N, C]
     labels, _ = propagate_labels_batched(feats.unsqueeze(0), first.unsqueeze(0), n_last_frames,
-                                         size_mask_neighborhood, topk, want_hard=False)
+                                         size_mask_neighborhood, topk, want_hard=False, check=True)
     out = labels[0, 1:].permute(0, 2, 1).reshape(fs - 1, Cc, sr, sr).to(torch.float64)
     if dev_out.type != "cuda":
         out = out.to(dev_out)
@@ -362,9 +382,12 @@ def label_propagation(size_mask_neighborhood, topk, model, frame_tar, list_frame
     Cc = segs.shape[1]
     labels = torch.empty((1, ncontext + 1, N, Cc), dtype=torch.float32, device=feats.device)
     labels[0, :ncontext] = segs.reshape(ncontext, Cc, N).permute(0, 2, 1).float()
-    plan = FFPlan(1, ncontext + 1, sr, sr, D, Cc, max(ncontext, 1), size_mask_neighborhood, topk,
+    # contexts of target `ncontext` = frame 0 + the n_last previous frames: n_last = ncontext - 1 selects all of them
+    # (and keeps the reference's 8-context call inside the tensor-core engine's n_last <= 7)
+    plan = FFPlan(1, ncontext + 1, sr, sr, D, Cc, max(ncontext - 1, 1), size_mask_neighborhood, topk,
                   t_begin=ncontext, device=feats.device)
     plan.propagate(feats.unsqueeze(0), labels, None, FF_AUTO)
+    plan.check_complete()
     seg_tar = labels[0, ncontext].t().reshape(1, Cc, sr, sr).to(torch.float64)
     if size_mask_neighborhood > 0 and mask_neighborhood is None:                         # :424-428
         mask_neighborhood = restrict_neighborhood(sr, sr, size_mask_neighborhood).unsqueeze(0).expand(ncontext, -1, -1)

@@ -10,7 +10,6 @@ CUDA path: the unit of work bench.py times and smoke() checks.
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 
