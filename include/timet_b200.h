@@ -69,6 +69,26 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
                    int world_size, timet_comm_t comm, float *q_out, void *workspace,
                    size_t workspace_bytes, timet_stream_t stream);
 
+/* Extended form.  opts may be NULL (= timet_sinkhorn).
+ *   out_block_rows / out_block_stride: row j of Q is written at q_out + (j / out_block_rows) * out_block_stride +
+ *     (j % out_block_rows) * K floats (out_block_rows <= 0: contiguous).  With out_block_rows = N and out_block_stride =
+ *     n_frames * N * K the assignment of clip b lands in frame 0 of the channel-last label tensor of
+ *     timet_ff_propagate -- TimeT.make_seg_maps' reshape + the first_seg copy (time_tuning.py:144-147) disappear.
+ *   share_sm: run the resident kernel with 512 instead of 1024 threads per CTA so that kernels launched on another
+ *     stream (the HBM/L2-bound Feature-Forwarding stages) can co-reside on the SMs; the call is latency-bound. */
+typedef struct timet_sinkhorn_opts {
+    int64_t out_block_rows;
+    int64_t out_block_stride;
+    int32_t share_sm;
+    int32_t reserved;
+} timet_sinkhorn_opts;
+int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
+                      timet_comm_t comm, float *q_out, const timet_sinkhorn_opts *opts, void *workspace,
+                      size_t workspace_bytes, timet_stream_t stream);
+/* 1 if a call of this shape runs as ONE resident kernel (rows of exp(S/eps) fit the SMs' shared memory), 0 if it runs
+ * as one streaming pass per iteration */
+int timet_sinkhorn_resident(int64_t B, int K);
+
 /* ------------------------------------------------------------------ cosine scores
  * No-grad branch of TimeT.get_feature_prototype_similarity (time_tuning.py:130-141):
  *   scores[B, K] = F.normalize(x[B, dh], dim=-1) @ prototypes[K, dh]^T      (float32 in / out)
@@ -77,6 +97,11 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
 size_t timet_cosine_scores_workspace_bytes(int64_t B, int K, int dh);
 int timet_cosine_scores(const float *x, const float *prototypes, int64_t B, int K, int dh, float *scores_out,
                         void *workspace, size_t workspace_bytes, timet_stream_t stream);
+/* Several feature blocks of rows_each rows against the same prototypes in ONE GEMM launch (get_loss scores the source
+ * and the target frame, time_tuning.py:268,275): scores_out is [n_x * rows_each, K], block i at row i * rows_each;
+ * n_x <= 4; workspace sized for B = n_x * rows_each. */
+int timet_cosine_scores_multi(const float *const *x_list, int n_x, int64_t rows_each, const float *prototypes, int K, int dh,
+                              float *scores_out, void *workspace, size_t workspace_bytes, timet_stream_t stream);
 
 /* ------------------------------------------------------------------ Feature-Forwarding
  * Stands behind  label_propagation(...)  mask_propagation.py:396-445   (one target frame)
@@ -117,6 +142,10 @@ typedef struct timet_ff_params {
 size_t timet_ff_workspace_bytes(const timet_ff_params *p);
 /* 1 if the tensor-core engine supports this shape (radius 1..15, n_last_frames <= 7, ...) */
 int timet_ff_tc_supported(const timet_ff_params *p);
+/* FLOPs the tensor-core kernel issues for this problem (key tiles inside the window band only, M padded to the
+ * 128-row MMA): the numerator of the tensor-pipe roofline in bench.py.  0 if the TC engine does not support the shape.
+ * For comparison, the dense definition of SURVEY.md §8d is 2 * N^2 * dim * sum_t ctx(t) per clip. */
+double timet_ff_tc_executed_flops(const timet_ff_params *p);
 
 /* stage 1: L2-normalise rows (F.normalize, :418-419) -> fp32 + fp16 copies in the workspace */
 int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspace, size_t workspace_bytes,

@@ -1,10 +1,11 @@
 """Import the UNMODIFIED reference (SMSD75/Timetuning) in place from /root/reference.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``timetuning_b200/`` may import this.
-Used by ``oracle/make_golden.py`` (fixture generation, build container only) and
-by the ``-m "not gpu"`` tests that cross-check the numpy oracle against the live
-reference when ``/root/reference`` is present.  ``/root/reference`` does not exist
-on the GPU box; callers must check :func:`available` first.
+Used by ``oracle/make_golden.py`` (fixture generation, build container only), by the
+tests that cross-check against the live reference, and by ``bench.py``'s reference arm.
+``/root/reference`` does not exist on the GPU box: there the git-ignored copy
+``baseline/_ref/`` made by ``oracle/make_ref.py`` (it travels with the ``gpurun``
+snapshot) is used; callers must check :func:`available` first and skip cleanly.
 
 Recipe: the reference's modules import eight third-party roots that
 are absent here and never touched by the hot path; they are replaced by MagicMock
@@ -21,7 +22,21 @@ import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get("TIMET_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIPPED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")       # oracle/make_ref.py (git-ignored copy)
+
+
+def _find_root() -> str:
+    env = os.environ.get("TIMET_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _SHIPPED):
+        if os.path.isfile(os.path.join(cand, "mask_propagation.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _STUB_ROOTS = ("timm", "faiss", "skimage", "mmcv", "matplotlib", "nbformat",
                "pytorch_lightning", "torchmetrics", "wandb", "tensorboard")
 _loaded: dict[str, types.ModuleType] = {}

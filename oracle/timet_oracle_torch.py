@@ -58,6 +58,14 @@ def propagate_frame(radius, topk, sr, feat_tar, ctx_feats, ctx_segs, mask):
 
 
 @torch.no_grad()
+def propagate_labels(n_last, radius, topk, sr, feats, first_seg, mask):
+    """Eval call pattern (mask_propagation.py:821): first_seg [1, C, H, W] at any resolution (nearest-resized, :456);
+    returns the list of fs-1 maps [C, sr, sr] float64."""
+    first = F.interpolate(first_seg.double(), size=(sr, sr), mode="nearest")            # :456
+    return propagate_clip(n_last, radius, topk, sr, feats, first, mask)
+
+
+@torch.no_grad()
 def propagate_clip(n_last, radius, topk, sr, feats, first_seg, mask):
     """mask_propagation.py:448-496: feats [fs, N, D], first_seg [1, C, sr, sr] float64."""
     first_feat = feats[0].T

@@ -81,15 +81,51 @@ def test_spatial_resolution_duck_typing():
     class Wrapper:
         feature_extractor = FE()
 
-    assert ops._spatial_resolution(FE()) == 28
-    assert ops._spatial_resolution(Wrapper()) == 28
+    assert ops._spatial_resolution(FE()) == (28, 28)
+    assert ops._spatial_resolution(Wrapper()) == (28, 28)
+
+    class NonSquare:
+        spatial_resolution = (60, 106)       # additive: DAVIS 480x854 at patch 8
+    assert ops._spatial_resolution(NonSquare()) == (60, 106)
 
 
-def test_install_binds_reference_attributes():
+def test_install_binds_the_real_reference_modules_and_uninstall_restores_them():
+    """install() against the reference's own modules (imported in place / from the shipped copy): the names the
+    reference resolves at call time (time_tuning.py:49,51,147,165; mask_propagation.py:485,821) are rebound, and
+    uninstall() puts the originals back.  Binding only -- no compute without a GPU."""
+    import ref_loader
+    import timetuning_b200 as tb
+    from timetuning_b200 import training
+    if not ref_loader.available():
+        pytest.skip("reference not available (neither /root/reference nor baseline/_ref)")
+    mu, mp, tt, _ = ref_loader.load()
+    orig = (tt.sinkhorn, tt.propagate_labels, mp.label_propagation, mp.propagate_labels, mp.restrict_neighborhood,
+            mp.norm_mask, mu.sinkhorn, tt.TimeT.get_loss, tt.TimeT.get_scores)
+    assert tt.sinkhorn is mu.sinkhorn and tt.propagate_labels is mp.propagate_labels
+    inst = tb.install(tt, mp, mu, fast_get_loss=True)
+    try:
+        assert tt.sinkhorn is ops.sinkhorn and tt.propagate_labels is ops.propagate_labels
+        assert mp.label_propagation is ops.label_propagation and mp.norm_mask is ops.norm_mask
+        assert mp.propagate_labels is ops.propagate_labels and mp.restrict_neighborhood is ops.restrict_neighborhood
+        assert mu.sinkhorn is ops.sinkhorn
+        assert tt.TimeT.get_loss is training.fast_get_loss and tt.TimeT.get_scores is training.get_scores
+        # the reference's own callers look the names up in their module globals at call time
+        assert tt.TimeT.find_optimal_assignment.__globals__["sinkhorn"] is ops.sinkhorn
+        assert tt.TimeT.make_seg_maps.__globals__["propagate_labels"] is ops.propagate_labels
+        assert mp.propagate_labels is not orig[3]
+    finally:
+        inst.uninstall()
+    now = (tt.sinkhorn, tt.propagate_labels, mp.label_propagation, mp.propagate_labels, mp.restrict_neighborhood,
+           mp.norm_mask, mu.sinkhorn, tt.TimeT.get_loss, tt.TimeT.get_scores)
+    assert all(a is b for a, b in zip(orig, now))
+
+
+def test_install_on_partial_modules():
     import types
     import timetuning_b200 as tb
-    tt, mp, mu = types.SimpleNamespace(), types.SimpleNamespace(), types.SimpleNamespace()
-    tb.install(tt, mp, mu)
-    assert tt.sinkhorn is ops.sinkhorn and tt.propagate_labels is ops.propagate_labels
-    assert mp.label_propagation is ops.label_propagation and mp.norm_mask is ops.norm_mask
-    assert mu.sinkhorn is ops.sinkhorn
+    tt = types.SimpleNamespace(sinkhorn=None, propagate_labels=None)
+    with tb.install(time_tuning=tt):
+        assert tt.sinkhorn is ops.sinkhorn and tt.propagate_labels is ops.propagate_labels
+    assert tt.sinkhorn is None and tt.propagate_labels is None
+    with pytest.raises(ValueError):
+        tb.install(fast_get_loss=True)

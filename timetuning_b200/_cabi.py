@@ -14,6 +14,11 @@ from . import _build
 _lib = None
 
 
+class SinkhornOpts(C.Structure):
+    """struct timet_sinkhorn_opts"""
+    _fields_ = [("out_block_rows", C.c_int64), ("out_block_stride", C.c_int64), ("share_sm", C.c_int32), ("reserved", C.c_int32)]
+
+
 class FFParams(C.Structure):
     """struct timet_ff_params"""
     _fields_ = [("n_clips", C.c_int32), ("n_frames", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32),
@@ -30,10 +35,14 @@ _PROTOS = {
     "timet_debug_reload_env": (C.c_int, []),
     "timet_sinkhorn_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "timet_sinkhorn": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "timet_sinkhorn_ex": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
+    "timet_sinkhorn_resident": (C.c_int, [C.c_int64, C.c_int]),
     "timet_cosine_scores_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "timet_cosine_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "timet_cosine_scores_multi": (C.c_int, [_P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "timet_ff_workspace_bytes": (C.c_size_t, [C.POINTER(FFParams)]),
     "timet_ff_tc_supported": (C.c_int, [C.POINTER(FFParams)]),
+    "timet_ff_tc_executed_flops": (C.c_double, [C.POINTER(FFParams)]),
     "timet_ff_prepare": (C.c_int, [C.POINTER(FFParams), _P, _P, C.c_size_t, _P]),
     "timet_ff_select": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, C.c_size_t, _P]),
     "timet_ff_select_timed": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, C.c_size_t, _P, _P, _P]),

@@ -49,6 +49,11 @@ int timet_ff_tc_supported(const timet_ff_params *p) {
     return ff_tc_supported(*p) ? 1 : 0;
 }
 
+double timet_ff_tc_executed_flops(const timet_ff_params *p) {
+    if (ff_validate(p) != TIMET_OK) return 0.0;
+    return ff_tc_executed_flops(*p);
+}
+
 int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspace, size_t workspace_bytes,
                      timet_stream_t stream) {
     FFLayout L;

@@ -503,6 +503,32 @@ bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
 }
 
 
+// FLOPs the tensor-core kernel ISSUES for this problem (what the tensor pipe executes): every key tile inside a
+// query tile's window band, M padded to the 128-row MMA, N = the tile's key columns, K = Dp.  0 if unsupported.
+double ff_tc_executed_flops(const timet_ff_params &p) {
+    TcGeom G;
+    const FFLayout L = ff_layout(p);
+    if (!tc_geometry(p, L, &G)) return 0.0;
+    double total = 0.0;
+    for (int t = p.t_begin; t < p.n_frames; ++t) {
+        const int nctx = ctx_count(t, p.n_last_frames);
+        for (int qt = 0; qt < G.tiles_per_frame; ++qt) {
+            const int qr0 = qt * G.QR, qr1 = (G.H - 1 < qr0 + G.QR - 1) ? G.H - 1 : qr0 + G.QR - 1;
+            const int kr_lo = (qr0 - G.radius > 0) ? qr0 - G.radius : 0;
+            const int kr_hi = (G.H - 1 < qr1 + G.radius) ? G.H - 1 : qr1 + G.radius;
+            const int nchunks = (kr_hi - kr_lo + G.RPC) / G.RPC;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                int rc = kr_hi + 1 - (kr_lo + ch * G.RPC);
+                if (rc > G.RPC) rc = G.RPC;
+                int n_mma = (rc + G.qrows - 1) / G.qrows * G.qrows * G.W;
+                if (n_mma > G.NT) n_mma = G.NT;
+                total += (double)nctx * 2.0 * 128.0 * n_mma * G.Dp;
+            }
+        }
+    }
+    return total * p.n_clips;
+}
+
 bool ff_tc_supported(const timet_ff_params &p) {
     TcGeom G;
     const FFLayout L = ff_layout(p);

@@ -17,13 +17,20 @@ namespace timet {
 constexpr int SC_THREADS = 192;       // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
 constexpr int SC_STAGES = 4;
 
+constexpr int SC_MAX_INPUTS = 4;
+struct ScInputs {
+    const float *x[SC_MAX_INPUTS];     // n row blocks of rows_each rows; output rows are their concatenation
+    int64_t rows_each;
+};
+
 __global__ void __launch_bounds__(256)
-scores_prep_kernel(const float *__restrict__ x, __half *__restrict__ out, int64_t rows, int dh, int dhp, int normalize) {
+scores_prep_kernel(ScInputs in, __half *__restrict__ out, int64_t rows, int dh, int dhp, int normalize) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t row = warp; row < rows; row += nwarps) {
-        const float *src = x + row * dh;
+        const int64_t blk = row / in.rows_each;
+        const float *src = in.x[blk] + (row - blk * in.rows_each) * dh;
         float ss = 0.f;
         for (int i = lane; i < dh; i += 32) { const float v = src[i]; ss = fmaf(v, v, ss); }
         ss = warp_sum(ss);
@@ -154,8 +161,20 @@ size_t timet_cosine_scores_workspace_bytes(int64_t B, int K, int dh) {
 
 int timet_cosine_scores(const float *x, const float *prototypes, int64_t B, int K, int dh, float *scores_out,
                         void *workspace, size_t workspace_bytes, timet_stream_t stream) {
-    TIMET_CHECK_ARG(x && prototypes && scores_out && workspace, "cosine_scores: NULL pointer");
-    TIMET_CHECK_ARG(B >= 1 && K >= 1 && dh >= 1 && dh <= 4096, "cosine_scores: bad shape B=%lld K=%d dh=%d", (long long)B, K, dh);
+    const float *xs[1] = {x};
+    return timet_cosine_scores_multi(xs, 1, B, prototypes, K, dh, scores_out, workspace, workspace_bytes, stream);
+}
+
+int timet_cosine_scores_multi(const float *const *x_list, int n_x, int64_t rows_each, const float *prototypes, int K, int dh,
+                              float *scores_out, void *workspace, size_t workspace_bytes, timet_stream_t stream) {
+    TIMET_CHECK_ARG(x_list && prototypes && scores_out && workspace, "cosine_scores: NULL pointer");
+    TIMET_CHECK_ARG(n_x >= 1 && n_x <= SC_MAX_INPUTS, "cosine_scores: n_x=%d must be in 1..%d", n_x, SC_MAX_INPUTS);
+    ScInputs in;
+    in.rows_each = rows_each;
+    for (int i = 0; i < SC_MAX_INPUTS; ++i) in.x[i] = (i < n_x) ? x_list[i] : nullptr;
+    for (int i = 0; i < n_x; ++i) TIMET_CHECK_ARG(x_list[i] != nullptr, "cosine_scores: input %d is NULL", i);
+    const int64_t B = rows_each * n_x;
+    TIMET_CHECK_ARG(rows_each >= 1 && K >= 1 && dh >= 1 && dh <= 4096, "cosine_scores: bad shape B=%lld K=%d dh=%d", (long long)B, K, dh);
     TIMET_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "cosine_scores: workspace must be 1024-byte aligned");
     if (workspace_bytes < scores_ws_bytes(B, K, dh)) {
         set_error("cosine_scores: workspace %zu < %zu bytes", workspace_bytes, scores_ws_bytes(B, K, dh));
@@ -170,9 +189,13 @@ int timet_cosine_scores(const float *x, const float *prototypes, int64_t B, int 
     int64_t pb = (B + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (pb > cap) pb = cap;
-    scores_prep_kernel<<<(int)pb, 256, 0, st>>>(x, a2, B, dh, dhp, 1);
+    scores_prep_kernel<<<(int)pb, 256, 0, st>>>(in, a2, B, dh, dhp, 1);
     TIMET_LAUNCHED();
-    scores_prep_kernel<<<(K + 7) / 8, 256, 0, st>>>(prototypes, b2, K, dh, dhp, 0);      // prototypes are used as given (:138,:140)
+    ScInputs pin;
+    pin.rows_each = K;
+    pin.x[0] = prototypes;
+    for (int i = 1; i < SC_MAX_INPUTS; ++i) pin.x[i] = nullptr;
+    scores_prep_kernel<<<(K + 7) / 8, 256, 0, st>>>(pin, b2, K, dh, dhp, 0);      // prototypes are used as given (:138,:140)
     TIMET_LAUNCHED();
 
     const int n_tiles = (int)((K + 255) / 256);

@@ -23,9 +23,19 @@ constexpr int SK_THREADS = 512;
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_MAX_V4 = 4;   // float4 chunks per lane -> K <= 512 on the vector path
 
+// Row j of Q goes to q_out + (j / block_rows) * block_stride + (j % block_rows) * K  (block_rows <= 0: contiguous).
+// Lets a caller have the assignment written straight into frame 0 of the channel-last label tensor
+// [clip, frame, N, K] (block_rows = N, block_stride = n_frames * N * K): no copy between Sinkhorn and Feature-Forwarding.
+__device__ __forceinline__ float *sk_out_row(float *q_out, int64_t row, int K, int64_t block_rows, int64_t block_stride) {
+    if (block_rows <= 0) return q_out + row * K;
+    const int64_t blk = row / block_rows;
+    return q_out + blk * block_stride + (row - blk * block_rows) * K;
+}
+
 struct SkArgs {
     const float *in;
     float *q_out;
+    int64_t out_block_rows, out_block_stride;
     float *partials;      // [grid, K]
     float *R;             // [K] marginals produced by this pass
     const float *R_prev;  // [K] marginals of the previous pass (nullptr in pass 0)
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(SK_THREADS) sk_pass_vec(SkArgs A) {
                 }
             } else {
                 const float inv = __fdiv_rn(1.f, s);
-                float4 *dst = reinterpret_cast<float4 *>(A.q_out + row * K);
+                float4 *dst = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row, K, A.out_block_rows, A.out_block_stride));
 #pragma unroll
                 for (int v = 0; v < NV4; ++v) {
                     const int i4 = lane + 32 * v;
@@ -200,6 +210,7 @@ __global__ void __launch_bounds__(SK_THREADS) sk_pass_scalar(SkArgs A) {
         s = warp_sum(s);
         const float b = (MODE == 1) ? __fdiv_rn(A.c, s) : 1.f;
         const float inv = (MODE == 2) ? __fdiv_rn(1.f, s) : 0.f;
+        float *qrow = (MODE == 2 && live) ? sk_out_row(A.q_out, row, K, A.out_block_rows, A.out_block_stride) : nullptr;
         // sweep: warps add their row to the CTA marginal one after another (fixed order)
         for (int w = 0; w < SK_WARPS; ++w) {
             if (w == warp && live) {
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(SK_THREADS) sk_pass_scalar(SkArgs A) {
                     if (A.scores_mode) e = expf(e * A.inv_eps);
                     if (MODE == 0) red[i] += e;
                     else if (MODE == 1) red[i] = fmaf(e, b, red[i]);
-                    else A.q_out[row * K + i] = e * a_s[i] * inv;
+                    else qrow[i] = e * a_s[i] * inv;
                 }
             }
             if (MODE != 2) __syncthreads();
@@ -241,8 +252,9 @@ __global__ void sk_fill(float *p, int n, float v) {
 // of Q.  Per iteration: one sweep over shared memory, per-CTA marginal partials to global
 // (double-buffered), a grid barrier, and a fixed-order fold of all partials by every CTA
 // (bit-reproducible, identical on every CTA).
-constexpr int SKR_THREADS = 1024;
-constexpr int SKR_WARPS = SKR_THREADS / 32;
+// Thread count of the resident kernel: 1024 (32 warps; the whole register file of the SM) by default; 512 when the
+// caller wants to SHARE the SMs with other kernels running on another stream (half the register file and 1536 thread
+// slots stay free: the HBM/L2-bound Feature-Forwarding kernels co-reside; the Sinkhorn call is latency-bound anyway).
 constexpr int SKR_RED = 16;           // rows of the cross-warp reduction scratch (warps fold in SKR_WARPS / SKR_RED rounds)
 // Every CTA adds its K marginal partials to K global fixed-point accumulators per iteration.  Packed, the 200 accumulators
 // of config 2 share 13 cache lines and the 29 600 atomics of an iteration serialise in a handful of L2 slices; with one
@@ -257,6 +269,7 @@ constexpr int SKR_CNT_BITS = 16;
 struct SkResArgs {
     const float *in;
     float *q_out;
+    int64_t out_block_rows, out_block_stride;
     float *partials;          // [2, grid, K]
     unsigned int *bar;        // monotonic grid-barrier counter (zeroed before launch)
     unsigned long long *ufix; // [2, K * ustride] fixed-point marginal accumulators with arrival counts (zeroed before launch)
@@ -292,7 +305,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int tar
 
 // Deterministic cross-warp sum of per-lane column partials: warps fold into SKR_RED scratch rows in
 // SKR_WARPS / SKR_RED ordered rounds; afterwards column i = sum of red[0..SKR_RED) [i].
-template <int NV4>
+template <int NV4, int SKR_WARPS>
 __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[NV4], int K, int K4, int warp, int lane) {
     for (int round = 0; round < SKR_WARPS / SKR_RED; ++round) {
         if ((warp / SKR_RED) == round) {
@@ -317,6 +330,7 @@ __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[N
 // the world_size vectors in rank order (bit-identical on all ranks).  `vec` (shared memory, [K]) holds the local
 // vector on entry and the global sum on exit.  A slot is reused after 3 exchanges; a peer can only be one exchange
 // ahead, so it is never overwritten while still being read.
+template <int SKR_THREADS>
 __device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long long e, float *vec) {
     const int K = A.K;
     P2PBuf *own = reinterpret_cast<P2PBuf *>(A.peers[A.rank]);
@@ -362,8 +376,9 @@ __device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long l
     __syncthreads();
 }
 
-template <int NV4>
-__global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
+template <int NV4, int SKR_THREADS>
+__global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_resident(SkResArgs A) {   // <= 64 registers either way
+    constexpr int SKR_WARPS = SKR_THREADS / 32;
     extern __shared__ float4 smem4[];
     const int K = A.K, K4 = K >> 2;
     float4 *E = smem4;                                                   // [rows_per_cta, K4]
@@ -397,7 +412,7 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
     }
 
     // ---- R^(0) = column sums of E: per-CTA float partials, grid barrier, fixed-order fold -> a_i = r / R_i
-    skr_fold_warps<NV4>(red, acc, K, K4, warp, lane);
+    skr_fold_warps<NV4, SKR_WARPS>(red, acc, K, K4, warp, lane);
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
         float t = 0.f;
 #pragma unroll
@@ -407,7 +422,7 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
     grid_barrier(A.bar, (++epoch) * gridDim.x);
     fold_partials<SKR_THREADS>(A.partials, gridDim.x, K, red, a_s, 0.f);      // a_s = local column sums
     unsigned long long xch = A.epoch0;
-    if (A.ws > 1) skr_exchange(A, xch++, a_s);
+    if (A.ws > 1) skr_exchange<SKR_THREADS>(A, xch++, a_s);
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) a_s[i] = __fdiv_rn(A.r, a_s[i]);
     __syncthreads();
 
@@ -463,8 +478,8 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
             } else {
                 const float inv = __fdiv_rn(1.f, s);
                 const float inv2 = two ? __fdiv_rn(1.f, s2) : 0.f;
-                float4 *dst = reinterpret_cast<float4 *>(A.q_out + (row0 + rl) * K);
-                float4 *dst2 = reinterpret_cast<float4 *>(A.q_out + (row0 + rl2) * K);
+                float4 *dst = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + rl, K, A.out_block_rows, A.out_block_stride));
+                float4 *dst2 = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + (two ? rl2 : rl), K, A.out_block_rows, A.out_block_stride));
 #pragma unroll
                 for (int v = 0; v < NV4; ++v) {
                     const int i4 = lane + 32 * v;
@@ -477,11 +492,11 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
         // ---- marginals of Q itself, u_i = sum_j a_i E_ji b_j (they sum to 1 over i, so the fixed point never
         // overflows): integer atomics are associative -> the grid-wide sum is bit-reproducible without a fold.
         // The add carries the arrival (+1 in the low 16 bits); each column's thread polls its own accumulator.
-        skr_fold_warps<NV4>(red, acc, K, K4, warp, lane);
+        skr_fold_warps<NV4, SKR_WARPS>(red, acc, K, K4, warp, lane);
         unsigned long long *ufix = A.ufix + (size_t)(it & 1) * K * A.ustride;
         const unsigned long long want = (unsigned long long)((it >> 1) + 1) * gridDim.x;     // arrivals after this iteration
         float u_mine = 0.f;
-        const int i = threadIdx.x;                                    // K <= 512 < SKR_THREADS: one column per thread
+        const int i = threadIdx.x;                                    // K <= 512 <= SKR_THREADS: one column per thread
         if (i < K) {
             float t = 0.f;
 #pragma unroll
@@ -511,7 +526,7 @@ __global__ void __launch_bounds__(SKR_THREADS, 1) sk_resident(SkResArgs A) {
         __syncthreads();                                               // everyone is done with the fold scratch
         if (i < K) red[i] = u_mine;
         __syncthreads();
-        if (A.ws > 1) skr_exchange(A, xch++, red);                     // u_i summed over ranks (my_utils.py:270-272)
+        if (A.ws > 1) skr_exchange<SKR_THREADS>(A, xch++, red);                     // u_i summed over ranks (my_utils.py:270-272)
         if (i < K) a_s[i] = a_s[i] * __fdiv_rn(A.r, red[i]);           // Q *= r / u  (my_utils.py:268)
         __syncthreads();
     }
@@ -529,13 +544,17 @@ static bool sk_resident_plan(int64_t B, int K, int *grid, int *rows_per_cta, siz
     return true;
 }
 
-template <int NV4>
-static int sk_resident_launch(SkResArgs &A, int grid, size_t smem, cudaStream_t st) {
-    TIMET_CUDA(cudaFuncSetAttribute(sk_resident<NV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int NV4, int NT>
+static int sk_resident_launch_nt(SkResArgs &A, int grid, size_t smem, cudaStream_t st) {
+    TIMET_CUDA(cudaFuncSetAttribute(sk_resident<NV4, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {&A};
-    TIMET_CUDA(cudaLaunchCooperativeKernel((const void *)sk_resident<NV4>, dim3(grid), dim3(SKR_THREADS), args, smem, st));
+    TIMET_CUDA(cudaLaunchCooperativeKernel((const void *)sk_resident<NV4, NT>, dim3(grid), dim3(NT), args, smem, st));
     launch_counter()++;
     return TIMET_OK;
+}
+template <int NV4>
+static int sk_resident_launch(SkResArgs &A, int grid, size_t smem, cudaStream_t st, bool share_sm) {
+    return share_sm ? sk_resident_launch_nt<NV4, 512>(A, grid, smem, st) : sk_resident_launch_nt<NV4, 1024>(A, grid, smem, st);
 }
 
 static int sk_grid(int64_t B) {
@@ -548,7 +567,7 @@ template <int MODE>
 static int sk_launch(const SkArgs &A, int grid, cudaStream_t st) {
     const int K = A.K;
     const bool vec = (K % 4 == 0) && (K <= 128 * SK_MAX_V4) && ((reinterpret_cast<uintptr_t>(A.in) & 15) == 0) &&
-                     (A.q_out == nullptr || (reinterpret_cast<uintptr_t>(A.q_out) & 15) == 0);
+                     (A.q_out == nullptr || (reinterpret_cast<uintptr_t>(A.q_out) & 15) == 0) && (A.out_block_stride % 4) == 0;
     if (vec) {
         const size_t smem = (size_t)(K + SK_WARPS * K) * sizeof(float);
         const int nv4 = (K / 4 + 31) / 32;
@@ -588,7 +607,24 @@ size_t timet_sinkhorn_workspace_bytes(int64_t B, int K) {
 
 int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
                    timet_comm_t comm, float *q_out, void *workspace, size_t workspace_bytes, timet_stream_t stream) {
+    return timet_sinkhorn_ex(in, B, K, input_kind, epsilon, iters, world_size, comm, q_out, nullptr, workspace, workspace_bytes, stream);
+}
+
+int timet_sinkhorn_resident(int64_t B, int K) {
+    int g, rpc;
+    size_t smem;
+    return (B >= 1 && K >= 1 && sk_resident_plan(B, K, &g, &rpc, &smem) && g <= 160) ? 1 : 0;
+}
+
+int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
+                      timet_comm_t comm, float *q_out, const timet_sinkhorn_opts *opts, void *workspace, size_t workspace_bytes,
+                      timet_stream_t stream) {
     TIMET_CHECK_ARG(in && q_out && workspace, "sinkhorn: NULL pointer");
+    const int64_t ob_rows = opts ? opts->out_block_rows : 0, ob_stride = opts ? opts->out_block_stride : 0;
+    const bool share_sm = opts && opts->share_sm;
+    TIMET_CHECK_ARG(ob_rows <= 0 || (ob_stride >= ob_rows * K && B % ob_rows == 0),
+                    "sinkhorn: output blocks of %lld rows with stride %lld do not tile B=%lld rows of K=%d", (long long)ob_rows,
+                    (long long)ob_stride, (long long)B, K);
     TIMET_CHECK_ARG(B >= 1 && K >= 1, "sinkhorn: bad shape B=%lld K=%d", (long long)B, K);
     TIMET_CHECK_ARG(iters >= 0, "sinkhorn: iters=%d must be >= 0", iters);
     TIMET_CHECK_ARG(input_kind == TIMET_SK_EXP || input_kind == TIMET_SK_SCORES, "sinkhorn: bad input_kind %d", input_kind);
@@ -609,7 +645,7 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
         unsigned long long *pepoch = nullptr;
         const bool p2p = world_size > 1 && comm_p2p_info(comm, &peers, &prank, &pws, &pepoch) && pws == world_size && K <= P2P_MAX_K;
         if ((world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
-            (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160 &&
+            (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && (ob_stride % 4) == 0 && sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160 &&
             (int64_t)(iters / 2 + 1) * rgrid < (1 << SKR_CNT_BITS)) {      // arrival counts of a call fit their 16 bits
             float *partials = (float *)workspace;
             unsigned int *bar = (unsigned int *)(partials + (size_t)322 * K);
@@ -626,6 +662,7 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
             R.ufix_scale = ldexpf(1.0f, 47 - head);
             R.ufix_inv = ldexpf(1.0f, head - 47);
             R.ufix = (unsigned long long *)((char *)workspace + ufix_off);
+            R.out_block_rows = ob_rows; R.out_block_stride = ob_stride;
             R.in = in; R.q_out = q_out; R.partials = partials; R.bar = bar; R.B = B; R.K = K; R.iters = iters;
             R.rows_per_cta = rpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
             R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
@@ -635,10 +672,10 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
             R.timeout_ns = (unsigned long long)(E.p2p_timeout_s * 1e9);
             if (p2p) *pepoch += (unsigned long long)iters;             // pass 0 + (iters - 1) iterations exchange a vector
             switch ((K / 4 + 31) / 32) {
-                case 1: return sk_resident_launch<1>(R, rgrid, rsmem, st);
-                case 2: return sk_resident_launch<2>(R, rgrid, rsmem, st);
-                case 3: return sk_resident_launch<3>(R, rgrid, rsmem, st);
-                default: return sk_resident_launch<4>(R, rgrid, rsmem, st);
+                case 1: return sk_resident_launch<1>(R, rgrid, rsmem, st, share_sm);
+                case 2: return sk_resident_launch<2>(R, rgrid, rsmem, st, share_sm);
+                case 3: return sk_resident_launch<3>(R, rgrid, rsmem, st, share_sm);
+                default: return sk_resident_launch<4>(R, rgrid, rsmem, st, share_sm);
             }
         }
     }
@@ -651,6 +688,7 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
 
     SkArgs A;
     A.in = in; A.q_out = q_out; A.partials = partials; A.ticket = ticket;
+    A.out_block_rows = ob_rows; A.out_block_stride = ob_stride;
     A.B = B; A.K = K;
     A.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
     A.scores_mode = (input_kind == TIMET_SK_SCORES);

@@ -20,7 +20,7 @@ import ctypes as C
 import torch
 
 from . import _cabi
-from ._cabi import FFParams, FF_AUTO, FF_EXACT, FF_TC, SK_EXP, SK_SCORES, check
+from ._cabi import FFParams, FF_AUTO, FF_EXACT, FF_TC, SK_EXP, SK_SCORES, SinkhornOpts, check
 
 AFF_TEMPERATURE = 0.1          # mask_propagation.py:422
 _comm = {"handle": None, "world_size": 1, "rank": 0, "p2p": False}
@@ -52,12 +52,15 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return buf[off:off + nbytes]
 
 
-def _spatial_resolution(model) -> int:
-    """Duck-typed exactly like mask_propagation.py:402-405 / :452-455."""
+def _spatial_resolution(model):
+    """Duck-typed exactly like mask_propagation.py:402-405 / :452-455.  Returns (h, w): the reference's integer
+    ``spatial_resolution`` means a square grid (:407); a (h, w) pair is accepted additively for non-square grids
+    (DAVIS 480x854 frames), which restrict_neighborhood (:377) already allows."""
     fe = getattr(model, "feature_extractor", None)
-    if fe is not None and hasattr(fe, "spatial_resolution"):
-        return int(fe.spatial_resolution)
-    return int(model.spatial_resolution)
+    sr = fe.spatial_resolution if (fe is not None and hasattr(fe, "spatial_resolution")) else model.spatial_resolution
+    if isinstance(sr, (tuple, list)):
+        return int(sr[0]), int(sr[1])
+    return int(sr), int(sr)
 
 
 # --------------------------------------------------------------------------- Sinkhorn
@@ -78,18 +81,28 @@ def sinkhorn(Q: torch.Tensor, nmb_iters: int, world_size: int = 1) -> torch.Tens
 
 
 @torch.no_grad()
-def sinkhorn_from_scores(scores: torch.Tensor, epsilon: float, nmb_iters: int, world_size: int = 1) -> torch.Tensor:
+def sinkhorn_from_scores(scores: torch.Tensor, epsilon: float, nmb_iters: int, world_size: int = 1, out=None,
+                         share_sm: bool = False) -> torch.Tensor:
     """Fused form of TimeT.find_optimal_assignment (time_tuning.py:157-168): exp(scores/eps) is
-    evaluated inside every pass and never stored.  scores [B, K] -> Q [B, K] float32."""
+    evaluated inside every pass and never stored.  scores [B, K] -> Q [B, K] float32.
+
+    out: optional CUDA float32 destination [n_blocks, block_rows, K] whose last two dims are contiguous (blocks may be
+    strided, e.g. ``labels[:, 0]`` of the channel-last label tensor [bs, fs, N, K]: the assignment of clip b is written
+    straight into frame 0, no copy before Feature-Forwarding).  share_sm: see timet_sinkhorn_ex."""
     if scores.dim() != 2:
         raise ValueError(f"scores must be [B, K], got {tuple(scores.shape)}")
     dev_in = scores.device
     S = _to_cuda(scores.detach()).float().contiguous()
-    out = _sinkhorn_launch(S, SK_SCORES, float(epsilon), nmb_iters, world_size)
-    return out if dev_in.type == "cuda" else out.to(dev_in)
+    res = _sinkhorn_launch(S, SK_SCORES, float(epsilon), nmb_iters, world_size, out, share_sm)
+    return res if dev_in.type == "cuda" else res.to(dev_in)
 
 
-def _sinkhorn_launch(x, kind, eps, iters, world_size):
+def sinkhorn_is_resident(B: int, K: int) -> bool:
+    """True if a call of this shape runs as ONE resident kernel (else one streaming pass per iteration)."""
+    return bool(_cabi.lib().timet_sinkhorn_resident(int(B), int(K)))
+
+
+def _sinkhorn_launch(x, kind, eps, iters, world_size, out=None, share_sm=False):
     lib = _cabi.lib()
     B, K = x.shape
     comm = None
@@ -98,12 +111,20 @@ def _sinkhorn_launch(x, kind, eps, iters, world_size):
             raise RuntimeError(f"sinkhorn(world_size={world_size}) needs timetuning_b200.dist.init_comm() first "
                                f"(communicator world size: {_comm['world_size']})")
         comm = _comm["handle"]
+    opts = SinkhornOpts(0, 0, 1 if share_sm else 0, 0)
     with torch.cuda.device(x.device):
-        out = torch.empty((B, K), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((B, K), dtype=torch.float32, device=x.device)
+        else:
+            if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 3 and out.shape[2] == K and out.stride(2) == 1
+                    and out.stride(1) == K and out.shape[0] * out.shape[1] == B):
+                raise ValueError(f"out must be CUDA float32 [n_blocks, block_rows, {K}] covering {B} rows with contiguous blocks, "
+                                 f"got shape {tuple(out.shape)} strides {tuple(out.stride())}")
+            opts.out_block_rows, opts.out_block_stride = out.shape[1], out.stride(0)
         nbytes = lib.timet_sinkhorn_workspace_bytes(B, K)
         ws = _workspace(nbytes, x.device)
-        check(lib.timet_sinkhorn(_ptr(x), B, K, kind, eps, int(iters), int(world_size), comm, _ptr(out), _ptr(ws),
-                                 nbytes, _stream()), "sinkhorn")
+        check(lib.timet_sinkhorn_ex(_ptr(x), B, K, kind, eps, int(iters), int(world_size), comm, _ptr(out), C.byref(opts), _ptr(ws),
+                                    nbytes, _stream()), "sinkhorn")
     return out
 
 
@@ -126,6 +147,27 @@ def cosine_scores(x: torch.Tensor, prototypes: torch.Tensor) -> torch.Tensor:
         ws = _workspace(nbytes, xc.device)
         check(lib.timet_cosine_scores(_ptr(xc), _ptr(pc), B, K, dh, _ptr(out), _ptr(ws), nbytes, _stream()), "cosine_scores")
     return out if dev_in.type == "cuda" else out.to(dev_in)
+
+
+@torch.no_grad()
+def cosine_scores_multi(xs, prototypes: torch.Tensor) -> torch.Tensor:
+    """cosine_scores for several equally shaped feature blocks [B, dh] against the same prototypes in ONE GEMM launch
+    (get_loss scores the source and the target frame, time_tuning.py:268,275).  Returns [len(xs) * B, K]."""
+    xs = [_to_cuda(x.detach()).float().contiguous() for x in xs]
+    pc = _to_cuda(prototypes.detach()).float().contiguous()
+    B, dh = xs[0].shape
+    if any(tuple(x.shape) != (B, dh) for x in xs) or pc.shape[1] != dh or not 1 <= len(xs) <= 4:
+        raise ValueError("cosine_scores_multi: 1..4 blocks of identical shape [B, dh] and prototypes [K, dh] expected")
+    K = pc.shape[0]
+    lib = _cabi.lib()
+    ptrs = (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    with torch.cuda.device(pc.device):
+        out = torch.empty((len(xs) * B, K), dtype=torch.float32, device=pc.device)
+        nbytes = int(lib.timet_cosine_scores_workspace_bytes(len(xs) * B, K, dh))
+        ws = _workspace(nbytes, pc.device)
+        check(lib.timet_cosine_scores_multi(ptrs, len(xs), B, _ptr(pc), K, dh, _ptr(out), _ptr(ws), nbytes, _stream()),
+              "cosine_scores_multi")
+    return out
 
 
 # --------------------------------------------------------------------------- small routines
@@ -174,21 +216,52 @@ def _upsample_argmax_cl(frames_cl, h, w, out_h, out_w, dev_out=None):
     return out if dev_out is None or dev_out.type == "cuda" else out.to(dev_out)
 
 
+def one_hot_first_seg(annotation: torch.Tensor, n_dims: int) -> torch.Tensor:
+    """mask_propagation.to_one_hot (:349-361) + unsqueeze(0), the first_seg of the eval call (:821), on the annotation's
+    device: int labels [1, H, W] -> one-hot float32 [1, C, H, W].  (stays PyTorch.)"""
+    return torch.nn.functional.one_hot(annotation[0].long(), int(n_dims)).permute(2, 0, 1).unsqueeze(0).float()
+
+
 @torch.no_grad()
-def propagate_labels_eval(n_last_frames, size_mask_neighborhood, topk, feats, first_seg, input_resolution):
+def propagate_labels_eval(n_last_frames, size_mask_neighborhood, topk, feats, first_seg, input_resolution,
+                          engine=FF_AUTO, events=None, grid=None):
     """The whole eval call pattern of mask_propagation.py:821-824 for one video on the device: feats [fs, N, D]
-    backbone features, first_seg [1, C, H, W] (one-hot annotation of frame 0) -> int64 [fs-1, R, R] hard predictions
-    (labels stay channel-last float32 on the GPU; no float64 maps, no [T, C, R, R] tensor)."""
+    backbone features, first_seg [1, C, H, W] (one-hot annotation of frame 0) -> int64 [fs-1, R_h, R_w] hard predictions
+    (labels stay channel-last float32 on the GPU; no float64 maps, no [T, C, R, R] tensor).
+    grid=(h, w) for non-square patch grids (DAVIS 480x854 -> 60x106 at patch 8; additive, the reference is square-only);
+    input_resolution may then be a (height, width) pair."""
     feats = _to_cuda(feats.detach()).float().contiguous()
     fs, N, D = feats.shape
-    sr = int(round(N ** 0.5))
-    seg = torch.nn.functional.interpolate(_to_cuda(first_seg.detach()).to(torch.float64), size=(sr, sr), mode="nearest")
+    gh, gw = _grid_of(N, grid)
+    seg = torch.nn.functional.interpolate(_to_cuda(first_seg.detach()).to(torch.float64), size=(gh, gw), mode="nearest")
     Cc = seg.shape[1]
     first = seg[0].reshape(Cc, N).t().float()
     labels, _ = propagate_labels_batched(feats.unsqueeze(0), first.unsqueeze(0), n_last_frames, size_mask_neighborhood,
-                                         topk, want_hard=False)
-    R = int(input_resolution)
-    return _upsample_argmax_cl(labels[0, 1:], sr, sr, R, R)
+                                         topk, engine=engine, want_hard=False, events=events, grid=(gh, gw))
+    Rh, Rw = (int(input_resolution),) * 2 if isinstance(input_resolution, int) else (int(input_resolution[0]), int(input_resolution[1]))
+    pred = _upsample_argmax_cl(labels[0, 1:], gh, gw, Rh, Rw)
+    if events is not None:
+        events["tail1"] = _record()
+    return pred
+
+
+def _record():
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _grid_of(N, grid):
+    """(h, w) of the patch grid: the reference's square grid (mask_propagation.py:407) unless `grid` says otherwise."""
+    if grid is not None:
+        gh, gw = int(grid[0]), int(grid[1])
+        if gh * gw != N:
+            raise ValueError(f"grid {gh}x{gw} does not match {N} patches")
+        return gh, gw
+    sr = int(round(N ** 0.5))
+    if sr * sr != N:
+        raise ValueError(f"square patch grids only (mask_propagation.py:407) unless grid=(h, w) is given, got N={N}")
+    return sr, sr
 
 
 # --------------------------------------------------------------------------- Feature-Forwarding
@@ -212,9 +285,16 @@ class FFPlan:
     def tc_supported(self) -> bool:
         return bool(_cabi.lib().timet_ff_tc_supported(C.byref(self.params)))
 
-    def propagate(self, feats, labels, hard=None, engine=FF_AUTO):
+    @property
+    def tc_executed_flops(self) -> float:
+        """FLOPs the tensor-core kernel issues for one select() of this plan (0 if unsupported)."""
+        return float(_cabi.lib().timet_ff_tc_executed_flops(C.byref(self.params)))
+
+    def propagate(self, feats, labels, hard=None, engine=FF_AUTO, events=None):
         """feats fp32 [n_clips, n_frames, N, D]; labels fp32 [n_clips, n_frames, N, C] with frame(s)
-        < t_begin filled; writes frames >= t_begin in place and hard int64 [n_clips, N] if given."""
+        < t_begin filled; writes frames >= t_begin in place and hard int64 [n_clips, N] if given.
+        events: optional dict that receives CUDA timing events around the stages (prep0/prep1/tc0/tc1/select1/gather0/
+        gather1) -- the stages are then issued one by one; without it ONE C call runs all three."""
         p = self.params
         assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
         assert labels.is_cuda and labels.dtype == torch.float32 and labels.is_contiguous()
@@ -223,8 +303,21 @@ class FFPlan:
         if hard is not None:
             assert hard.is_cuda and hard.dtype == torch.int64 and hard.numel() == p.n_clips * self.N
         with torch.cuda.device(self.device):
-            check(_cabi.lib().timet_ff_propagate(C.byref(p), int(engine), _ptr(feats), _ptr(labels), _ptr(hard),
-                                                 _ptr(self.workspace), self.nbytes, _stream()), "ff_propagate")
+            if events is None:
+                check(_cabi.lib().timet_ff_propagate(C.byref(p), int(engine), _ptr(feats), _ptr(labels), _ptr(hard),
+                                                     _ptr(self.workspace), self.nbytes, _stream()), "ff_propagate")
+            else:
+                events["prep0"] = _record()
+                self.prepare(feats)
+                events["prep1"] = _record()
+                if engine != FF_EXACT and self.tc_supported:
+                    events["tc0"], events["tc1"] = _record(), _record()        # handles exist; the library re-records them
+                    self.select_timed(engine, events["tc0"], events["tc1"])
+                else:
+                    self.select(engine)
+                events["select1"] = events["gather0"] = _record()
+                self.gather(labels, hard)
+                events["gather1"] = _record()
         return labels
 
     def prepare(self, feats):
@@ -238,12 +331,14 @@ class FFPlan:
                                               _stream()), "ff_select")
 
     def select_timed(self, engine, ev_begin, ev_end):
-        """select() with two torch.cuda.Event(enable_timing=True) recorded by the library right around the
-        tensor-core nomination kernel (they must have been recorded once before so that their handles exist)."""
+        """select() with two torch.cuda.Event (either may be None) recorded by the library on the stream right before /
+        right after the tensor-core nomination kernel.  They must have been recorded once before so that their handles
+        exist.  Used to time the dominant kernel alone and to release a second stream as soon as that kernel is done."""
+        hb = C.c_void_p(ev_begin.cuda_event) if ev_begin is not None else C.c_void_p(0)
+        he = C.c_void_p(ev_end.cuda_event) if ev_end is not None else C.c_void_p(0)
         with torch.cuda.device(self.device):
             check(_cabi.lib().timet_ff_select_timed(C.byref(self.params), int(engine), _ptr(self.workspace), self.nbytes,
-                                                    _stream(), C.c_void_p(ev_begin.cuda_event), C.c_void_p(ev_end.cuda_event)),
-                  "ff_select_timed")
+                                                    _stream(), hb, he), "ff_select_timed")
 
     def gather(self, labels, hard=None):
         with torch.cuda.device(self.device):
@@ -304,28 +399,27 @@ def _plan(*key, device):
 
 @torch.no_grad()
 def propagate_labels_batched(feats, first_labels, n_last_frames=7, size_mask_neighborhood=6, topk=5,
-                             engine=FF_AUTO, want_hard=True, check=False):
+                             engine=FF_AUTO, want_hard=True, check=False, events=None, grid=None):
     """Additive fast entry: every clip of a batch in one call (replaces the per-clip Python loop of
     TimeT.get_loss, time_tuning.py:277-296).
 
     feats [bs, fs, N, D] float32 backbone features; first_labels [bs, N, C] (Sinkhorn Q of frame 0,
     channel-last as get_scores returns it).  Returns (labels [bs, fs, N, C] float32 with frame 0 =
-    first_labels, hard int64 [bs, sr, sr] = argmax of the last frame, or None)."""
+    first_labels, hard int64 [bs, h, w] = argmax of the last frame, or None).
+    grid=(h, w): non-square patch grids (additive; the reference supports square grids only, :407)."""
     feats = _to_cuda(feats).float().contiguous()
     first_labels = _to_cuda(first_labels).float()
     bs, fs, N, D = feats.shape
-    sr = int(round(N ** 0.5))
-    if sr * sr != N:
-        raise ValueError(f"square patch grids only (mask_propagation.py:407), got N={N}")
+    gh, gw = _grid_of(N, grid)
     Cc = first_labels.shape[-1]
-    plan = _plan(bs, fs, sr, sr, D, Cc, n_last_frames, size_mask_neighborhood, topk, device=feats.device)
+    plan = _plan(bs, fs, gh, gw, D, Cc, n_last_frames, size_mask_neighborhood, topk, device=feats.device)
     labels = torch.empty((bs, fs, N, Cc), dtype=torch.float32, device=feats.device)
     labels[:, 0] = first_labels.reshape(bs, N, Cc)
     hard = torch.empty((bs, N), dtype=torch.int64, device=feats.device) if want_hard else None
-    plan.propagate(feats, labels, hard, engine)
+    plan.propagate(feats, labels, hard, engine, events)
     if check:               # one small device->host read: only the drop-in shims pay for it by default
         plan.check_complete()
-    return labels, (hard.view(bs, sr, sr) if want_hard else None)
+    return labels, (hard.view(bs, gh, gw) if want_hard else None)
 
 
 @torch.no_grad()
@@ -335,7 +429,7 @@ def propagate_labels(n_last_frames, size_mask_neighborhood, topk, model, frame_l
     frame_list [fs, N, D] features (features_exist=True) or images [fs, 3, H, W]; first_seg
     [1, C, H, W].  Returns a list of fs-1 tensors [C, sr, sr], float64 like the reference (:443,:456),
     on the features' device."""
-    sr = _spatial_resolution(model)
+    gh, gw = _spatial_resolution(model)
     if features_exist:
         feats = frame_list
     else:   # the reference runs the backbone frame by frame (:411,:467); same call, batched by frame here
@@ -343,15 +437,15 @@ def propagate_labels(n_last_frames, size_mask_neighborhood, topk, model, frame_l
     dev_out = feats.device
     feats = _to_cuda(feats.detach()).float().contiguous()
     fs, N, D = feats.shape
-    if N != sr * sr:
-        raise ValueError(f"features have {N} patches but spatial_resolution is {sr}")
+    if N != gh * gw:
+        raise ValueError(f"features have {N} patches but spatial_resolution is {gh}x{gw}")
     seg = _to_cuda(first_seg.detach()).to(torch.float64)
-    seg = torch.nn.functional.interpolate(seg, size=(sr, sr), mode="nearest")            # :456
+    seg = torch.nn.functional.interpolate(seg, size=(gh, gw), mode="nearest")            # :456
     Cc = seg.shape[1]
     first = seg[0].reshape(Cc, N).t().float()                                            # channel-last [N, C]
     labels, _ = propagate_labels_batched(feats.unsqueeze(0), first.unsqueeze(0), n_last_frames,
-                                         size_mask_neighborhood, topk, want_hard=False, check=True)
-    out = labels[0, 1:].permute(0, 2, 1).reshape(fs - 1, Cc, sr, sr).to(torch.float64)
+                                         size_mask_neighborhood, topk, want_hard=False, check=True, grid=(gh, gw))
+    out = labels[0, 1:].permute(0, 2, 1).reshape(fs - 1, Cc, gh, gw).to(torch.float64)
     if dev_out.type != "cuda":
         out = out.to(dev_out)
     return [out[i] for i in range(fs - 1)]
@@ -366,7 +460,7 @@ def label_propagation(size_mask_neighborhood, topk, model, frame_tar, list_frame
     Returns (seg_tar [1, C, h, w] float64, feat_tar [D, N], mask_neighborhood).
     mask_neighborhood is only passed through (its content is assumed to be
     restrict_neighborhood(h, w, size_mask_neighborhood), as propagate_labels builds it)."""
-    sr = _spatial_resolution(model)
+    gh, gw = _spatial_resolution(model)
     if features_exist:
         features = frame_tar
     else:
@@ -384,13 +478,13 @@ def label_propagation(size_mask_neighborhood, topk, model, frame_tar, list_frame
     labels[0, :ncontext] = segs.reshape(ncontext, Cc, N).permute(0, 2, 1).float()
     # contexts of target `ncontext` = frame 0 + the n_last previous frames: n_last = ncontext - 1 selects all of them
     # (and keeps the reference's 8-context call inside the tensor-core engine's n_last <= 7)
-    plan = FFPlan(1, ncontext + 1, sr, sr, D, Cc, max(ncontext - 1, 1), size_mask_neighborhood, topk,
+    plan = FFPlan(1, ncontext + 1, gh, gw, D, Cc, max(ncontext - 1, 1), size_mask_neighborhood, topk,
                   t_begin=ncontext, device=feats.device)
     plan.propagate(feats.unsqueeze(0), labels, None, FF_AUTO)
     plan.check_complete()
-    seg_tar = labels[0, ncontext].t().reshape(1, Cc, sr, sr).to(torch.float64)
+    seg_tar = labels[0, ncontext].t().reshape(1, Cc, gh, gw).to(torch.float64)
     if size_mask_neighborhood > 0 and mask_neighborhood is None:                         # :424-428
-        mask_neighborhood = restrict_neighborhood(sr, sr, size_mask_neighborhood).unsqueeze(0).expand(ncontext, -1, -1)
+        mask_neighborhood = restrict_neighborhood(gh, gw, size_mask_neighborhood).unsqueeze(0).expand(ncontext, -1, -1)
     if dev_out.type != "cuda":
         seg_tar = seg_tar.to(dev_out)
     return seg_tar, return_feat_tar, mask_neighborhood

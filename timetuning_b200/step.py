@@ -6,6 +6,17 @@ CUDA path: the unit of work bench.py times and smoke() checks.
         -> Sinkhorn x2 (fused exp, one pass per iteration)
         -> batched Feature-Forwarding of Q_source over every clip
         -> (Q_source, Q_target, last-frame hard labels)
+
+Stream choreography (StepRunner, overlap=True).  The Sinkhorn chain does not depend on the affinity / top-k selection
+and vice versa; only the label gather needs Q_source.  So the chain runs on a second, high-priority stream:
+
+    main : prepare -> select (tcgen05 kernel, finalize) ------------------> [wait Q_source] -> gather
+    side :            [wait tcgen05 kernel done] -> cosine scores -> Sinkhorn(source) -> Sinkhorn(target)
+
+The resident Sinkhorn kernel is cooperative and wants every SM; the persistent tcgen05 kernel fills every SM's shared
+memory.  Racing them would leave one half-resident, so the side stream is released by an event recorded right after
+the tcgen05 kernel; it then co-resides (512-thread variant, half the register file) with the L2-bound finalize and gather
+kernels, which leave the tensor pipe and most issue slots idle.
 """
 from __future__ import annotations
 
@@ -20,14 +31,103 @@ def ff_sinkhorn_step(head_src, head_tgt, backbone, prototypes, n_last_frames=7, 
     """head_src/head_tgt [bs, N, dh], backbone [bs, fs, N, D], prototypes [K, dh] — CUDA float32.
     Returns (batch_q [bs,N,K], target_q [bs,N,K], hard int64 [bs,sr,sr], labels [bs,fs,N,K])."""
     bs, N, dh = head_src.shape
-    scores_src = ops.cosine_scores(head_src.reshape(bs * N, dh), prototypes)                  # :136-140 (no-grad branch)
-    scores_tgt = ops.cosine_scores(head_tgt.reshape(bs * N, dh), prototypes)
-    q_src = ops.sinkhorn_from_scores(scores_src, epsilon, sinkhorn_iterations, world_size)   # :164-165
-    q_tgt = ops.sinkhorn_from_scores(scores_tgt, epsilon, sinkhorn_iterations, world_size)
-    K = q_src.shape[1]
-    labels, hard = ops.propagate_labels_batched(backbone, q_src.view(bs, N, K), n_last_frames,
-                                                size_mask_neighborhood, topk, engine=engine)
-    return q_src.view(bs, N, K), q_tgt.view(bs, N, K), hard, labels
+    fs, D = backbone.shape[1], backbone.shape[3]
+    sr = int(round(N ** 0.5))
+    runner = _runner(bs, fs, sr, D, dh, prototypes.shape[0], n_last_frames, size_mask_neighborhood, topk, epsilon,
+                     sinkhorn_iterations, world_size, engine, backbone.device)
+    q_src, q_tgt, hard = runner.run(head_src, head_tgt, backbone, prototypes)
+    labels = runner.labels.clone()                 # the runner reuses its buffers: hand out copies
+    return labels[:, 0], q_tgt.clone(), hard.clone(), labels
+
+
+_runners: dict = {}
+
+
+def _runner(*key):
+    r = _runners.get(key)
+    if r is None:
+        if len(_runners) > 4:
+            _runners.clear()
+        *args, world_size, engine, device = key
+        r = _runners[key] = StepRunner(*args, world_size=world_size, engine=engine, device=device)
+    return r
+
+
+class StepRunner:
+    """Device-resident FF + Sinkhorn step with its buffers, plan and streams kept across calls."""
+
+    def __init__(self, bs, fs, sr, D, dh, K, n_last_frames=7, size_mask_neighborhood=6, topk=5, epsilon=0.05,
+                 sinkhorn_iterations=10, world_size=1, engine=ops.FF_AUTO, overlap=True, device=None):
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.bs, self.fs, self.sr, self.N, self.D, self.dh, self.K = bs, fs, sr, sr * sr, D, dh, K
+        self.eps, self.iters, self.world_size, self.engine = float(epsilon), int(sinkhorn_iterations), int(world_size), engine
+        self.plan = ops._plan(bs, fs, sr, sr, D, K, n_last_frames, size_mask_neighborhood, topk, device=self.device)
+        self.labels = torch.empty((bs, fs, self.N, K), dtype=torch.float32, device=self.device)
+        self.hard = torch.empty((bs, self.N), dtype=torch.int64, device=self.device)
+        self.q_tgt = torch.empty((bs, self.N, K), dtype=torch.float32, device=self.device)
+        self.sinkhorn_resident = ops.sinkhorn_is_resident(bs * self.N, K)
+        # the choreography above needs the one-launch resident Sinkhorn kernel and the tensor-core engine's event hook
+        self.overlap = bool(overlap) and self.sinkhorn_resident and engine != ops.FF_EXACT and self.plan.tc_supported
+        with torch.cuda.device(self.device):
+            self.side = torch.cuda.Stream(device=self.device, priority=-1) if self.overlap else None
+            self.ev_tc_done = torch.cuda.Event()
+            self.ev_tc_done.record()                   # materialise the cudaEvent_t handle (the library re-records it)
+            self.ev_q_src = torch.cuda.Event()
+            self.ev_side_done = torch.cuda.Event()
+            self.ev_inputs = torch.cuda.Event()
+
+    def _sinkhorn_chain(self, head_src, head_tgt, prototypes, events, share_sm):
+        bs, N, K = self.bs, self.N, self.K
+        if events is not None:
+            events["scores0"] = ops._record()
+        scores = ops.cosine_scores_multi([head_src.reshape(bs * N, self.dh), head_tgt.reshape(bs * N, self.dh)], prototypes)
+        if events is not None:
+            events["scores1"] = ops._record()
+        # Q_source is written straight into frame 0 of the channel-last label tensor (time_tuning.py:144-147 without a copy)
+        ops.sinkhorn_from_scores(scores[:bs * N], self.eps, self.iters, self.world_size, out=self.labels[:, 0], share_sm=share_sm)
+        self.ev_q_src.record()
+        ops.sinkhorn_from_scores(scores[bs * N:], self.eps, self.iters, self.world_size, out=self.q_tgt, share_sm=share_sm)
+        if events is not None:
+            events["sinkhorn1"] = ops._record()
+
+    @torch.no_grad()
+    def run(self, head_src, head_tgt, backbone, prototypes, events=None):
+        """head_src/head_tgt [bs, N, dh], backbone [bs, fs, N, D], prototypes [K, dh]: CUDA float32, contiguous.
+        Returns (q_src [bs,N,K] = a view of labels[:, 0], q_tgt [bs,N,K], hard int64 [bs,sr,sr]).  The buffers are
+        reused by the next call.  events: optional dict receiving CUDA timing events of the stages."""
+        plan, engine = self.plan, self.engine
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            if not self.overlap:
+                self._sinkhorn_chain(head_src, head_tgt, prototypes, events, share_sm=False)
+                plan.propagate(backbone, self.labels, self.hard, engine, events)
+            else:
+                self.ev_inputs.record(main)
+                if events is not None:
+                    events["prep0"] = ops._record()
+                plan.prepare(backbone)
+                ev_tc_done = self.ev_tc_done
+                if events is not None:
+                    events["prep1"] = ops._record()
+                    events["tc0"], events["tc1"] = ops._record(), ops._record()
+                    ev_tc_done = events["tc1"]
+                    plan.select_timed(engine, events["tc0"], ev_tc_done)
+                    events["select1"] = ops._record()
+                else:
+                    plan.select_timed(engine, None, ev_tc_done)     # recorded by the library right after the tcgen05 kernel
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(self.ev_inputs)       # inputs ready, previous step's gather finished with labels
+                    self.side.wait_event(ev_tc_done)           # never race the persistent tcgen05 kernel for the SMs
+                    self._sinkhorn_chain(head_src, head_tgt, prototypes, events, share_sm=True)
+                    self.ev_side_done.record(self.side)
+                main.wait_event(self.ev_q_src)
+                if events is not None:
+                    events["gather0"] = ops._record()
+                plan.gather(self.labels, self.hard)
+                if events is not None:
+                    events["gather1"] = ops._record()
+                main.wait_event(self.ev_side_done)             # q_tgt complete before the caller's stream goes on
+        return self.labels[:, 0], self.q_tgt, self.hard.view(self.bs, self.sr, self.sr)
 
 
 class HostStepPipeline:
@@ -46,6 +146,7 @@ class HostStepPipeline:
         self.d_head = torch.empty((2, bs, N, dh), dtype=torch.float32, device=self.device)
         self.d_backbone = torch.empty((bs, fs, N, D), dtype=torch.float32, device=self.device)
         self.labels = torch.empty((bs, fs, N, K), dtype=torch.float32, device=self.device)
+        self.q_tgt = torch.empty((bs, N, K), dtype=torch.float32, device=self.device)
         self.hard = torch.empty((bs, N), dtype=torch.int64, device=self.device)
         self.hard_host = torch.empty((bs, N), dtype=torch.int64).pin_memory()
         self.ev_head = torch.cuda.Event()
@@ -70,9 +171,8 @@ class HostStepPipeline:
                 self.ev_chunk[c].record(self.copy_stream)
         main.wait_event(self.ev_head)
         scores = ops.cosine_scores(self.d_head.reshape(2 * bs * N, self.dh), prototypes)
-        q_src = ops.sinkhorn_from_scores(scores[:bs * N], epsilon, sinkhorn_iterations, world_size)
-        q_tgt = ops.sinkhorn_from_scores(scores[bs * N:], epsilon, sinkhorn_iterations, world_size)
-        self.labels[:, 0] = q_src.view(bs, N, K)
+        ops.sinkhorn_from_scores(scores[:bs * N], epsilon, sinkhorn_iterations, world_size, out=self.labels[:, 0])
+        ops.sinkhorn_from_scores(scores[bs * N:], epsilon, sinkhorn_iterations, world_size, out=self.q_tgt)
         plan = ops._plan(cb, self.fs, sr, sr, self.D, K, n_last_frames, size_mask_neighborhood, topk, device=self.device)
         for c in range(self.chunks):
             main.wait_event(self.ev_chunk[c])
@@ -80,4 +180,4 @@ class HostStepPipeline:
                            self.hard[c * cb:(c + 1) * cb], engine)
         self.hard_host.copy_(self.hard, non_blocking=True)
         self.ev_done.record(main)
-        return q_src.view(bs, N, K), q_tgt.view(bs, N, K), self.hard_host.view(bs, sr, sr)
+        return self.labels[:, 0], self.q_tgt, self.hard_host.view(bs, sr, sr)
