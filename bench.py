@@ -75,7 +75,8 @@ def parse():
     ap.add_argument("--cpu-impl", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--serial", action="store_true", help="one stream, no overlap of the Sinkhorn chain with Feature-Forwarding")
+    ap.add_argument("--overlap", action="store_true", help="run the cosine-scores + Sinkhorn chain on a second stream under the "
+                    "Feature-Forwarding kernels (measured: no gain, see profiles/r2_experiments.md); default is one stream")
     return ap.parse_args()
 
 
@@ -377,7 +378,7 @@ def main():
         torch.cuda.synchronize()
 
     runner = StepRunner(bs, fs, sr, D, cfg["head_dim"], K, cfg["n_last"], cfg["radius"], cfg["topk"], EPSILON, ITERS,
-                        world_size=world, engine=engine, overlap=not args.serial, device=dev) if not is_eval else None
+                        world_size=world, engine=engine, overlap=args.overlap, device=dev) if not is_eval else None
     host = {k: torch.from_numpy(v).pin_memory() for k, v in x.items() if k != "prototypes"}
     d_in = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     d_pr = torch.from_numpy(x["prototypes"]).to(dev) if not is_eval else None
@@ -532,7 +533,7 @@ def main():
                                  "bytes_model": "(iters+2)*B*K*4 per call, 2 calls (streaming model, SURVEY.md §8d); the resident "
                                                 "kernel's real DRAM traffic is the compulsory 2*B*K*4",
                                  "compulsory_gbs": 2 * 2 * B * K * 4 / (stage_ms["sinkhorn_x2"] * 1e-3) / 1e9,
-                                 "note": "runs on a second stream under the Feature-Forwarding kernels unless --serial" if not args.serial else "serial"}
+                                 "note": "second stream under the Feature-Forwarding kernels" if args.overlap else "same stream"}
         if "gather" in stage_ms:
             gather_bytes = clips_per_launch * ((fs - 1) * N * K * 4 + N * K * 4)
             extra["gather"] = {"bound": "hbm", "achieved": gather_bytes / (stage_ms["gather"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
@@ -573,7 +574,7 @@ def main():
                                         "accumulation and every nominated key is re-evaluated in f32 (bit-identical to the f32 engine)"
                            if engine_used == "tcgen05" else "f32",
                            "l2": "inputs larger than L2 (backbone features %.0f MB per step)" % (d_in["backbone"].numel() * 4 / 1e6),
-                           "streams": "serial" if (args.serial or is_eval) else "cosine scores + Sinkhorn on a second stream, joined before the gather",
+                           "streams": "cosine scores + Sinkhorn on a second stream, joined before the gather" if (args.overlap and not is_eval) else "one stream",
                            "parallelism": par},
                 "e2e": e2e, "gpu_launches": launches, "roofline": roof, "stage_ms": stage_ms, "stage_roofline": extra,
                 "ff_stats": st, "clocks": clock_info, "cpu_baseline": cpu, "sinkhorn_path": sk_path}

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TIMET_ABI_VERSION 1
+#define TIMET_ABI_VERSION 2
 
 typedef void *timet_stream_t; /* cudaStream_t */
 typedef void *timet_comm_t;   /* opaque: owns an ncclComm_t */
@@ -147,16 +147,18 @@ int timet_ff_tc_supported(const timet_ff_params *p);
  * For comparison, the dense definition of SURVEY.md §8d is 2 * N^2 * dim * sum_t ctx(t) per clip. */
 double timet_ff_tc_executed_flops(const timet_ff_params *p);
 
-/* stage 1: L2-normalise rows (F.normalize, :418-419) -> fp32 + fp16 copies in the workspace */
+/* stage 1: one pass over the feature rows (F.normalize, :418-419): inverse norms + the fp16 tensor-core operand go to
+ * the workspace.  No normalised fp32 copy is made: stage 2 reads `feats` IN PLACE for the exact fp32 similarity, so the
+ * same buffer must be passed to timet_ff_select and stay unchanged until that has run.  feats must be 16-byte aligned. */
 int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspace, size_t workspace_bytes,
                      timet_stream_t stream);
 /* stage 2: per (clip, target frame, query): window mask, exp(sim/T), global top-k over all
  * contexts with ties kept, normalised weights (:422-436) -> sparse (weight, key) lists in the workspace */
-int timet_ff_select(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+int timet_ff_select(const timet_ff_params *p, int engine, const float *feats, void *workspace, size_t workspace_bytes,
                     timet_stream_t stream);
 /* timet_ff_select with two caller-created cudaEvent_t (may be NULL) recorded on `stream` immediately before and
  * after the tensor-core nomination kernel: lets a caller time the dominant kernel alone without a profiler. */
-int timet_ff_select_timed(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+int timet_ff_select_timed(const timet_ff_params *p, int engine, const float *feats, void *workspace, size_t workspace_bytes,
                           timet_stream_t stream, void *event_before_nominate, void *event_after_nominate);
 /* stage 3: frame-sequential weighted gather of the context labels (:439-444) and argmax */
 int timet_ff_gather(const timet_ff_params *p, float *labels, int64_t *hard, const void *workspace,

@@ -21,7 +21,7 @@ def header_functions():
 def test_library_builds_and_loads():
     lib = _cabi.lib()
     assert os.path.isfile(_build.LIB)
-    assert lib.timet_abi_version() == 1
+    assert lib.timet_abi_version() == 2
 
 
 def test_every_declared_symbol_is_exported_and_bound():

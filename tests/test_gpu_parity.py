@@ -290,7 +290,8 @@ def test_host_pipeline_matches_device_step():
     for _ in range(2):
         q2, t2, h2 = pipe.run(pin[0], pin[1], pin[2], protos)
     torch.cuda.synchronize()
-    assert torch.equal(q1, q2) and torch.equal(t1, t2)
+    # same kernels, same launch shapes -> same bits (the scores GEMM sees the two heads as one [2*B, dh] matrix in both)
+    assert torch.equal(q1, q2) and torch.equal(t1, t2), ((q1 - q2).abs().max().item(), (t1 - t2).abs().max().item())
     assert torch.equal(h1.cpu(), h2)
 
 

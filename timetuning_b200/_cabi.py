@@ -44,8 +44,8 @@ _PROTOS = {
     "timet_ff_tc_supported": (C.c_int, [C.POINTER(FFParams)]),
     "timet_ff_tc_executed_flops": (C.c_double, [C.POINTER(FFParams)]),
     "timet_ff_prepare": (C.c_int, [C.POINTER(FFParams), _P, _P, C.c_size_t, _P]),
-    "timet_ff_select": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, C.c_size_t, _P]),
-    "timet_ff_select_timed": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, C.c_size_t, _P, _P, _P]),
+    "timet_ff_select": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, _P, C.c_size_t, _P]),
+    "timet_ff_select_timed": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, _P, C.c_size_t, _P, _P, _P]),
     "timet_ff_gather": (C.c_int, [C.POINTER(FFParams), _P, _P, _P, C.c_size_t, _P]),
     "timet_ff_propagate": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "timet_ff_stats": (C.c_int, [C.POINTER(FFParams), _P, C.c_size_t, _P, _P]),
@@ -85,7 +85,7 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(handle, name)    # AttributeError if the ABI lost a symbol
             fn.restype, fn.argtypes = res, args
-        if handle.timet_abi_version() != 1:
+        if handle.timet_abi_version() != 2:
             raise RuntimeError("libtimet_b200 ABI version mismatch")
         _lib = handle
     return _lib

@@ -51,6 +51,8 @@ struct EnvCfg {
     bool tc_pair, tc_persist, tc_dyn, tc_trace;
     bool sk_streaming;
     int sk_ustride;                                                // 0 = default
+    int gather_batch;                                              // gather: label rows in flight per batch (0 = by topk)
+    int fin_batch;                                                 // finalize: candidate rows in flight per batch (0 = by topk)
     double p2p_timeout_s;                                          // peer-exchange / marginal wait time-out (seconds)
 };
 const EnvCfg &env_cfg();
@@ -80,7 +82,7 @@ struct FFLayout {
     int N, Dp, nT, kw;               // patches, padded dim (multiple of 64), target frames, slots per query
     int64_t rows;                    // n_clips * n_frames * N feature rows
     int64_t queries;                 // n_clips * nT * N
-    size_t off_fn32, off_fn16, off_sel_w, off_sel_k, off_sel_cnt, off_cand, off_cand_meta, off_stats, off_redo, off_trace;
+    size_t off_xpad, off_inv, off_fn16, off_sel_w, off_sel_k, off_sel_cnt, off_cand, off_cand_meta, off_stats, off_redo, off_trace;
     size_t off_wide_w, off_wide_k;   // overflow pool for rows with more than kw kept entries (exact tie sets)
     int64_t wide_cap;                // pool capacity in entries
     size_t total;
@@ -98,7 +100,10 @@ static inline FFLayout ff_layout(const timet_ff_params &p) {
     L.queries = (int64_t)p.n_clips * L.nT * L.N;
     size_t o = 0;
     // +256 rows of slack: TMA boxes of the last query/key tile may run past the last row
-    L.off_fn32 = o; o = align_up(o + (size_t)(L.rows + 256) * L.Dp * sizeof(float), 1024);
+    // fp32 operands of the exact re-evaluation: the CALLER's feature rows are read in place (no normalised fp32 copy);
+    // one inverse norm per row.  Only when dim % 4 != 0 (rows not float4-addressable) a zero-padded copy is kept.
+    L.off_xpad = o; o = align_up(o + ((p.dim & 3) ? (size_t)L.rows * L.Dp * sizeof(float) : 0), 1024);
+    L.off_inv = o; o = align_up(o + (size_t)L.rows * sizeof(float), 1024);
     L.off_fn16 = o; o = align_up(o + (size_t)(L.rows + 256) * L.Dp * sizeof(__half), 1024);
     L.off_sel_w = o; o = align_up(o + (size_t)L.queries * L.kw * sizeof(float), 1024);
     L.off_sel_k = o; o = align_up(o + (size_t)L.queries * L.kw * sizeof(int32_t), 1024);
@@ -119,10 +124,25 @@ static inline FFLayout ff_layout(const timet_ff_params &p) {
 
 int ff_validate(const timet_ff_params *p);
 
+// fp32 view of the feature rows for the exact (canonical) similarity: row r = x + r * ld, its first n4 float4 are
+// meaningful; inv[r] = 1 / max(||row r||, 1e-12)
+struct FFSrc {
+    const float *x;
+    const float *inv;
+    int ld, n4;
+};
+static inline FFSrc ff_src(const timet_ff_params &p, const FFLayout &L, const float *feats, const char *ws) {
+    FFSrc S;
+    S.inv = reinterpret_cast<const float *>(ws + L.off_inv);
+    if (p.dim & 3) { S.x = reinterpret_cast<const float *>(ws + L.off_xpad); S.ld = L.Dp; S.n4 = L.Dp >> 2; }
+    else { S.x = feats; S.ld = p.dim; S.n4 = p.dim >> 2; }
+    return S;
+}
+
 // stage launchers (defined in the per-stage .cu files)
 int ff_prepare_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st);
-int ff_select_exact_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
-int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
+int ff_select_exact_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st);
+int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st);
 int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
                      cudaStream_t st);
 bool ff_tc_supported(const timet_ff_params &p);
@@ -143,8 +163,11 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// Canonical fp32 dot product of two Dp-long rows (Dp % 64 == 0, n4 = Dp/4 float4 elements).
+// Canonical fp32 similarity of two feature rows (n4 float4 elements each, rows 16-byte aligned).
 // DEFINITION (every engine reproduces it bit for bit, so the tensor-core engine and the exact scan agree):
+//   sim(q, k) = (dot(x_q, x_k) * inv_q) * inv_k        inv = 1 / max(||x||_2, 1e-12)   (F.normalize, :418-419)
+// on the UN-normalised rows -- no normalised fp32 copy of the features exists (it would cost a 4*D-byte write and
+// re-read per row); the reference normalises first and multiplies after, which differs by a few ulp.  dot:
 //   partial[l], l = 0..31 : one fmaf chain over the float4 elements i = l, l+32, l+64, ... in that order,
 //                           components x, y, z, w in that order;
 //   result                : xor-butterfly tree  v[l] += v[l ^ 16]; v[l] += v[l ^ 8]; ... ; v[l] += v[l ^ 1].
@@ -177,6 +200,8 @@ __device__ __forceinline__ float dot_canonical_seq(const float4 *__restrict__ q,
     }
     return acc[0];
 }
+
+__device__ __forceinline__ float sim_from_dot(float dot, float inv_q, float inv_k) { return __fmul_rn(__fmul_rn(dot, inv_q), inv_k); }
 
 // exp(sim / T) exactly as mask_propagation.py:422 evaluates it in float32
 __device__ __forceinline__ float affinity_from_sim(float sim, float temperature) {

@@ -63,11 +63,12 @@ int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspa
     return ff_prepare_launch(*p, L, feats, (char *)workspace, (cudaStream_t)stream);
 }
 
-int timet_ff_select(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+int timet_ff_select(const timet_ff_params *p, int engine, const float *feats, void *workspace, size_t workspace_bytes,
                     timet_stream_t stream) {
     FFLayout L;
     int rc = check_ws(p, workspace, workspace_bytes, &L);
     if (rc != TIMET_OK) return rc;
+    TIMET_CHECK_ARG(feats != nullptr, "ff_select: feats is NULL (the exact re-evaluation reads the feature rows in place)");
     TIMET_CHECK_ARG(engine == TIMET_FF_EXACT || engine == TIMET_FF_TC || engine == TIMET_FF_AUTO, "ff_select: bad engine %d", engine);
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
@@ -80,9 +81,9 @@ int timet_ff_select(const timet_ff_params *p, int engine, void *workspace, size_
                       p->grid_h, p->grid_w, p->dim, p->radius, p->n_last_frames);
             return TIMET_ERR_UNSUPPORTED;
         }
-        return ff_select_tc_launch(*p, L, ws, st);
+        return ff_select_tc_launch(*p, L, feats, ws, st);
     }
-    return ff_select_exact_launch(*p, L, ws, st);
+    return ff_select_exact_launch(*p, L, feats, ws, st);
 }
 
 int timet_ff_gather(const timet_ff_params *p, float *labels, int64_t *hard, const void *workspace,
@@ -98,7 +99,7 @@ int timet_ff_propagate(const timet_ff_params *p, int engine, const float *feats,
                        void *workspace, size_t workspace_bytes, timet_stream_t stream) {
     int rc = timet_ff_prepare(p, feats, workspace, workspace_bytes, stream);
     if (rc != TIMET_OK) return rc;
-    rc = timet_ff_select(p, engine, workspace, workspace_bytes, stream);
+    rc = timet_ff_select(p, engine, feats, workspace, workspace_bytes, stream);
     if (rc != TIMET_OK) return rc;
     return timet_ff_gather(p, labels, hard, workspace, workspace_bytes, stream);
 }
@@ -170,11 +171,11 @@ int timet_debug_tc_trace(const timet_ff_params *p, const void *workspace, size_t
 }
 
 
-int timet_ff_select_timed(const timet_ff_params *p, int engine, void *workspace, size_t workspace_bytes,
+int timet_ff_select_timed(const timet_ff_params *p, int engine, const float *feats, void *workspace, size_t workspace_bytes,
                           timet_stream_t stream, void *event_before_nominate, void *event_after_nominate) {
     g_ev_nominate_begin = (cudaEvent_t)event_before_nominate;
     g_ev_nominate_end = (cudaEvent_t)event_after_nominate;
-    const int rc = timet_ff_select(p, engine, workspace, workspace_bytes, stream);
+    const int rc = timet_ff_select(p, engine, feats, workspace, workspace_bytes, stream);
     g_ev_nominate_begin = nullptr;
     g_ev_nominate_end = nullptr;
     return rc;

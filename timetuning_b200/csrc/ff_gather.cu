@@ -42,13 +42,51 @@ __device__ __forceinline__ void ga_fma(float4 &a, float w, const float4 l) {
     a.x = fmaf(w, l.x, a.x); a.y = fmaf(w, l.y, a.y); a.z = fmaf(w, l.z, a.z); a.w = fmaf(w, l.w, a.w);
 }
 
+// acc += sum_m w[m] * labels_row(k[m]) for the n_c (<= 32) entries held by the lanes of the warp (lane m: entry m).
+// GB gathered rows are in flight together (coherent L2 loads: earlier frames were written by other CTAs of this launch).
+template <typename V, int GB>
+__device__ __forceinline__ void ga_rows(V &acc0, V &acc1, float w_c, int32_t k_c, int n_c, const float *clip_base, int C, int c,
+                                        int c2, bool one, bool two) {
+    for (int m0 = 0; m0 < n_c; m0 += GB) {
+        float wm[GB];
+        V l0[GB], l1[GB];
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+            const int m = min(m0 + u, 31);
+            wm[u] = __shfl_sync(0xffffffffu, w_c, m);
+            const int32_t km = __shfl_sync(0xffffffffu, k_c, m);
+            const V *row = reinterpret_cast<const V *>(clip_base + (int64_t)km * C);
+            const bool on = m0 + u < n_c;
+            l0[u] = (on && one) ? __ldcg(row + c) : ga_zero<V>();
+            l1[u] = (on && two) ? __ldcg(row + c2) : ga_zero<V>();
+        }
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+            if (m0 + u < n_c) { ga_fma(acc0, wm[u], l0[u]); ga_fma(acc1, wm[u], l1[u]); }
+        }
+    }
+}
+
+// Wide rows are rare (degenerate features): kept out of line so that they do not cost the hot path registers.
+template <typename V>
+__device__ __noinline__ void ga_rows_wide(V &acc0, V &acc1, const float *__restrict__ wide_w, const int32_t *__restrict__ wide_k,
+                                          int wide_off, int n_row, const float *clip_base, int C, int c, int c2, bool one, bool two,
+                                          int lane) {
+    for (int base = 0; base < n_row; base += 32) {
+        const bool in = base + lane < n_row;
+        const float w_c = in ? __ldg(wide_w + wide_off + base + lane) : 0.f;
+        const int32_t k_c = in ? __ldg(wide_k + wide_off + base + lane) : 0;
+        ga_rows<V, 2>(acc0, acc1, w_c, k_c, min(32, n_row - base), clip_base, C, c, c2, one, two);
+    }
+}
+
 // V = float4 (C % 4 == 0) or float.  One WARP per query: lane m holds (weight, key) m of the sparse row,
 // broadcast by shuffle; every lane then owns channel vectors c = lane, lane+32, ... and issues the <= 4 gathered
 // row loads of a batch back to back (coherent L2 loads: earlier frames were written by other CTAs of this
 // launch).  The next query's sparse row is prefetched while the current one is gathered.
 // CLUSTER = false: the same body for ONE target frame per launch with `vcs` plain CTAs per clip (few clips: a
 // cluster of 8 CTAs per clip would leave most SMs idle; frames then cost one launch each).
-template <typename V, bool CLUSTER>
+template <typename V, bool CLUSTER, int GB>
 __global__ void __launch_bounds__(GA_THREADS, 2)
 ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const float *__restrict__ sel_w,
                  const int32_t *__restrict__ sel_k, const int32_t *__restrict__ sel_cnt, const float *__restrict__ wide_w,
@@ -82,40 +120,15 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
                 if (lane < kw) { w_n = __ldg(sel_w + (q0 + inext) * kw + lane); k_n = __ldg(sel_k + (q0 + inext) * kw + lane); }
             }
             V *dst = reinterpret_cast<V *>(clip_base + ((int64_t)t * N + i) * C);
-            // cnt < 0: wide row (more than kw survivors: exact tie sets) of -cnt entries in the pool at offset sel_k[0]
-            const int n_row = cnt < 0 ? -cnt : cnt;
-            const int wide_off = cnt < 0 ? __shfl_sync(0xffffffffu, k_l, 0) : 0;
             for (int c0 = 0; c0 < CV; c0 += 64) {          // warp-uniform: the shuffles below need every lane
                 const int c = c0 + lane, c2 = c + 32;
                 const bool one = c < CV, two = c2 < CV;
                 V acc0 = ga_zero<V>(), acc1 = ga_zero<V>();
-                for (int base = 0; base < n_row; base += 32) {
-                    float w_c = w_l;
-                    int32_t k_c = k_l;
-                    if (cnt < 0) {
-                        const bool in = base + lane < n_row;
-                        w_c = in ? __ldg(wide_w + wide_off + base + lane) : 0.f;
-                        k_c = in ? __ldg(wide_k + wide_off + base + lane) : 0;
-                    }
-                    const int n_c = min(32, n_row - base);
-                    for (int m0 = 0; m0 < n_c; m0 += 4) {
-                        float wm[4];
-                        V l0[4], l1[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int m = min(m0 + u, 31);
-                            wm[u] = __shfl_sync(0xffffffffu, w_c, m);
-                            const int32_t km = __shfl_sync(0xffffffffu, k_c, m);
-                            const V *row = reinterpret_cast<const V *>(clip_base + (int64_t)km * C);
-                            const bool on = m0 + u < n_c;
-                            l0[u] = (on && one) ? __ldcg(row + c) : ga_zero<V>();
-                            l1[u] = (on && two) ? __ldcg(row + c2) : ga_zero<V>();
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (m0 + u < n_c) { ga_fma(acc0, wm[u], l0[u]); ga_fma(acc1, wm[u], l1[u]); }
-                        }
-                    }
+                if (cnt >= 0) {
+                    ga_rows<V, GB>(acc0, acc1, w_l, k_l, cnt, clip_base, C, c, c2, one, two);
+                } else {
+                    // wide row (more than kw survivors: exact tie sets): -cnt entries in the pool at offset sel_k[0]
+                    ga_rows_wide<V>(acc0, acc1, wide_w, wide_k, __shfl_sync(0xffffffffu, k_l, 0), -cnt, clip_base, C, c, c2, one, two, lane);
                 }
                 if (one) dst[c] = acc0;
                 if (two) dst[c2] = acc1;
@@ -145,8 +158,9 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
     }
 }
 
-int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
-                     cudaStream_t st) {
+template <int GBSEL>
+static int ff_gather_launch_gb(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
+                               cudaStream_t st) {
     const float *sel_w = reinterpret_cast<const float *>(ws + L.off_sel_w);
     const int32_t *sel_k = reinterpret_cast<const int32_t *>(ws + L.off_sel_k);
     const int32_t *sel_cnt = reinterpret_cast<const int32_t *>(ws + L.off_sel_cnt);
@@ -171,10 +185,10 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         if (vec)
-            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4, true>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4, true, GBSEL>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                           L.nT, L.kw, tb, tb, nfr - 1, cs));
         else
-            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float, true>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float, true, 4>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                           L.nT, L.kw, tb, tb, nfr - 1, cs));
         TIMET_LAUNCHED();
         return TIMET_OK;
@@ -186,14 +200,24 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
     if (vcs < 1) vcs = 1;
     for (int t = tb; t < nfr; ++t) {
         if (vec)
-            ff_gather_kernel<float4, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            ff_gather_kernel<float4, false, GBSEL><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                                                                   L.nT, L.kw, tb, t, t, vcs);
         else
-            ff_gather_kernel<float, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            ff_gather_kernel<float, false, 4><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                                                                  L.nT, L.kw, tb, t, t, vcs);
         TIMET_LAUNCHED();
     }
     return TIMET_OK;
+}
+
+// Gathered rows in flight per batch: the usual survivor count (topk, no ties) should need ONE batch -- the kernel is
+// bound by dependent L2 round trips per query, not by bandwidth.  5 for the training default topk = 5, else 4.
+int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
+                     cudaStream_t st) {
+    const int gb = env_cfg().gather_batch ? env_cfg().gather_batch : (p.topk == 5 ? 5 : 4);
+    if (gb == 5) return ff_gather_launch_gb<5>(p, L, labels, hard, ws, st);
+    if (gb >= 7) return ff_gather_launch_gb<7>(p, L, labels, hard, ws, st);
+    return ff_gather_launch_gb<4>(p, L, labels, hard, ws, st);
 }
 
 }  // namespace timet

@@ -1,22 +1,21 @@
-// FF stage 1: L2-normalise every patch feature once per step.
+// FF stage 1: one pass over the features per step.
 //
 // Reference: F.normalize(feat, dim=D, p=2) on the target and on ALL context frames, recomputed
-// for every target frame (/root/reference/mask_propagation.py:418-419).  Here each row is
-// normalised once: x / max(||x||_2, 1e-12) in float32 (true division, like ATen), stored
-//   fn32 [rows, Dp] float32  — operand of the exact re-evaluation (dot_canonical)
-//   fn16 [rows, Dp] float16  — K-major operand of the tcgen05 nomination GEMM (TMA-loaded)
-// Dp = dim rounded up to 64, zero padded (zeros do not change any dot product bit).
-// HBM-bound: reads 4*D, writes 6*Dp bytes per row.  One warp per row, 128-bit accesses.
+// for every target frame (/root/reference/mask_propagation.py:418-419).  Here each row is visited once:
+//   inv  [rows]      float32  1 / max(||x||_2, 1e-12)         -- scales the exact fp32 similarity (common.cuh)
+//   fn16 [rows, Dp]  float16  x / max(||x||_2, 1e-12) rounded -- K-major operand of the tcgen05 nomination GEMM (TMA-loaded)
+// Dp = dim rounded up to 64, zero padded.  The fp32 rows themselves are NOT copied: the exact re-evaluation reads the
+// caller's tensor in place (only for dim % 4 != 0 a zero-padded fp32 copy is written so that rows are float4-addressable).
+// HBM-bound: reads 4*D, writes 2*Dp + 4 bytes per row.  One warp per row, 128-bit accesses.
 #include "common.cuh"
 
 namespace timet {
 
 constexpr int PREP_KEEP = 8;
 
-__device__ __forceinline__ void prep_store(float *d32, __half *d16, int i, float4 v, float denom) {
+__device__ __forceinline__ void prep_store(__half *d16, int i, float4 v, float denom) {
     v.x = __fdiv_rn(v.x, denom); v.y = __fdiv_rn(v.y, denom);
     v.z = __fdiv_rn(v.z, denom); v.w = __fdiv_rn(v.w, denom);
-    __stcs(reinterpret_cast<float4 *>(d32) + i, v);
     const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
     uint2 pk;
     pk.x = *reinterpret_cast<const uint32_t *>(&lo);
@@ -24,8 +23,9 @@ __device__ __forceinline__ void prep_store(float *d32, __half *d16, int i, float
     reinterpret_cast<uint2 *>(d16)[i] = pk;
 }
 
-__global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict__ feats, float *__restrict__ fn32,
-                                                         __half *__restrict__ fn16, int64_t rows, int dim, int Dp) {
+__global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict__ feats, float *__restrict__ xpad,
+                                                         float *__restrict__ inv, __half *__restrict__ fn16, int64_t rows,
+                                                         int dim, int Dp) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict
 #pragma unroll
                 for (int u = 0; u < PREP_KEEP; ++u) {
                     const int i = lane + 32 * u;
-                    keep[u] = (i < (dim >> 2)) ? __ldcs(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    keep[u] = (i < (dim >> 2)) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < PREP_KEEP; ++u)
@@ -57,14 +57,14 @@ __global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict
         }
         ss = warp_sum(ss);
         const float denom = fmaxf(sqrtf(ss), 1e-12f);
-        float *d32 = fn32 + row * Dp;
+        if (lane == 0) inv[row] = __fdiv_rn(1.0f, denom);
         __half *d16 = fn16 + row * Dp;
-        // Dp % 64 == 0 -> float4 / half2x2 stores are aligned
+        // Dp % 64 == 0 -> half2x2 stores are aligned
         if (cached) {
 #pragma unroll
             for (int u = 0; u < PREP_KEEP; ++u) {
                 const int i = lane + 32 * u;
-                if (i < (Dp >> 2)) prep_store(d32, d16, i, keep[u], denom);     // keep[u] is zero past dim
+                if (i < (Dp >> 2)) prep_store(d16, i, keep[u], denom);     // keep[u] is zero past dim
             }
         } else {
             for (int i = lane; i < (Dp >> 2); i += 32) {
@@ -77,20 +77,26 @@ __global__ void __launch_bounds__(256) ff_prepare_kernel(const float *__restrict
                     if (d + 1 < dim) v.y = src[d + 1];
                     if (d + 2 < dim) v.z = src[d + 2];
                     if (d + 3 < dim) v.w = src[d + 3];
+                    reinterpret_cast<float4 *>(xpad + row * Dp)[i] = v;     // float4-addressable copy of the raw row
                 }
-                prep_store(d32, d16, i, v, denom);
+                prep_store(d16, i, v, denom);
             }
         }
     }
 }
 
 int ff_prepare_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st) {
-    float *fn32 = reinterpret_cast<float *>(ws + L.off_fn32);
+    float *xpad = reinterpret_cast<float *>(ws + L.off_xpad);
+    float *inv = reinterpret_cast<float *>(ws + L.off_inv);
     __half *fn16 = reinterpret_cast<__half *>(ws + L.off_fn16);
+    if (!(p.dim & 3) && (reinterpret_cast<uintptr_t>(feats) & 15)) {
+        set_error("ff_prepare: feats must be 16-byte aligned (dim %% 4 == 0 rows are read in place as float4)");
+        return TIMET_ERR_INVALID;
+    }
     int64_t blocks = (L.rows + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    ff_prepare_kernel<<<(int)blocks, 256, 0, st>>>(feats, fn32, fn16, L.rows, p.dim, L.Dp);
+    ff_prepare_kernel<<<(int)blocks, 256, 0, st>>>(feats, xpad, inv, fn16, L.rows, p.dim, L.Dp);
     TIMET_LAUNCHED();
     // the 256 slack rows behind the last frame are read by out-of-range TMA boxes: keep them finite
     TIMET_CUDA(cudaMemsetAsync(fn16 + L.rows * L.Dp, 0, (size_t)256 * L.Dp * sizeof(__half), st));

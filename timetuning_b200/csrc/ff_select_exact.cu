@@ -25,7 +25,7 @@ struct WidePool {
 // exactly like the reference (mask_propagation.py:434-436: aff[aff < kth] = 0; aff /= aff.sum()).  Two passes over the
 // window (count + sum, then emit in scan order = context-major, window row-major: deterministic); the row lives in the
 // pool, its descriptor in the regular slots: sel_cnt = -n, sel_k[0] = pool offset.  Returns false if the pool is full.
-__device__ __forceinline__ bool ex_wide_row(const timet_ff_params &p, int N, int Dp, const float *__restrict__ fn32,
+__device__ __forceinline__ bool ex_wide_row(const timet_ff_params &p, int N, const FFSrc &S, float inv_q,
                                             const float4 *qs, int64_t clip_row0, int t, int r0, int c0, int wcols, int nwin,
                                             float theta, int lane, const WidePool &pool, float *__restrict__ w_out,
                                             int32_t *__restrict__ k_out, int32_t *__restrict__ cnt_out, int kw, int *n_out) {
@@ -39,7 +39,7 @@ __device__ __forceinline__ bool ex_wide_row(const timet_ff_params &p, int N, int
         int emitted = 0;
         for (int ci = 0; ci < nctx; ++ci) {
             const int f = ctx_frame(t, p.n_last_frames, ci);
-            const float *fbase = fn32 + (clip_row0 + (int64_t)f * N) * Dp;
+            const int64_t frow0 = clip_row0 + (int64_t)f * N;
             for (int m0 = 0; m0 < nwin; m0 += 32) {
                 const int m = m0 + lane;
                 float aff = -1.f;
@@ -47,7 +47,8 @@ __device__ __forceinline__ bool ex_wide_row(const timet_ff_params &p, int N, int
                 if (m < nwin) {
                     const int wr = m / wcols;
                     const int j = (r0 + wr) * W + c0 + (m - wr * wcols);
-                    const float sim = dot_canonical_seq(qs, reinterpret_cast<const float4 *>(fbase + (int64_t)j * Dp), Dp >> 2);
+                    const float dot = dot_canonical_seq(qs, reinterpret_cast<const float4 *>(S.x + (frow0 + j) * S.ld), S.n4);
+                    const float sim = sim_from_dot(dot, inv_q, __ldg(S.inv + frow0 + j));
                     aff = affinity_from_sim(sim, p.temperature);
                     key = f * N + j;
                 }
@@ -81,16 +82,16 @@ __device__ __forceinline__ bool ex_wide_row(const timet_ff_params &p, int N, int
 }
 
 __global__ void __launch_bounds__(EX_WARPS * 32)
-ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float *__restrict__ fn32,
+ff_select_exact_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw,
                        float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
                        unsigned long long *__restrict__ stats, const int32_t *__restrict__ qlist,
                        const unsigned int *__restrict__ qcount, int64_t n_queries, WidePool pool) {
-    extern __shared__ float4 qsm[];                       // [EX_WARPS][Dp/4]
+    extern __shared__ float4 qsm[];                       // [EX_WARPS][n4]
     __shared__ unsigned long long s_stat[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
     __syncthreads();
-    float4 *qs = qsm + (size_t)warp * (Dp >> 2);
+    float4 *qs = qsm + (size_t)warp * S.n4;
     const int H = p.grid_h, W = p.grid_w;
     const int64_t total = qlist ? (int64_t)*qcount : n_queries;
     const int64_t nwarps = (int64_t)gridDim.x * EX_WARPS;
@@ -105,8 +106,10 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
         const int64_t clip_row0 = (int64_t)clip * p.n_frames * N;
 
         __syncwarp();
-        const float4 *qrow = reinterpret_cast<const float4 *>(fn32 + (clip_row0 + (int64_t)t * N + i) * Dp);
-        for (int d = lane; d < (Dp >> 2); d += 32) qs[d] = qrow[d];
+        const int64_t q_row = clip_row0 + (int64_t)t * N + i;
+        const float4 *qrow = reinterpret_cast<const float4 *>(S.x + q_row * S.ld);
+        for (int d = lane; d < S.n4; d += 32) qs[d] = qrow[d];
+        const float inv_q = __ldg(S.inv + q_row);
         __syncwarp();
 
         const int qr = i / W, qc = i - qr * W;
@@ -122,7 +125,7 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
         const int nctx = ctx_count(t, p.n_last_frames);
         for (int ci = 0; ci < nctx; ++ci) {
             const int f = ctx_frame(t, p.n_last_frames, ci);
-            const float *fbase = fn32 + (clip_row0 + (int64_t)f * N) * Dp;
+            const int64_t frow0 = clip_row0 + (int64_t)f * N;
             for (int m0 = 0; m0 < nwin; m0 += 32) {
                 const int m = m0 + lane;
                 const bool valid = m < nwin;
@@ -131,7 +134,8 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
                 if (valid) {
                     const int wr = m / wcols;
                     const int j = (r0 + wr) * W + c0 + (m - wr * wcols);
-                    const float sim = dot_canonical_seq(qs, reinterpret_cast<const float4 *>(fbase + (int64_t)j * Dp), Dp >> 2);
+                    const float dot = dot_canonical_seq(qs, reinterpret_cast<const float4 *>(S.x + (frow0 + j) * S.ld), S.n4);
+                    const float sim = sim_from_dot(dot, inv_q, __ldg(S.inv + frow0 + j));
                     aff = affinity_from_sim(sim, p.temperature);
                     key = f * N + j;
                 }
@@ -146,7 +150,7 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
         bool done = false;
         if (m_list > kw || (m_list == 32 && L.dropped > 0)) {
             int n_wide = 0;
-            done = ex_wide_row(p, N, Dp, fn32, qs, clip_row0, t, r0, c0, wcols, nwin, L.kth, lane, pool, sel_w + qid * kw,
+            done = ex_wide_row(p, N, S, inv_q, qs, clip_row0, t, r0, c0, wcols, nwin, L.kth, lane, pool, sel_w + qid * kw,
                                sel_k + qid * kw, sel_cnt + qid, kw, &n_wide);
             if (done) { m = n_wide; st_wide += 1; st_sel += (unsigned long long)n_wide; }
             else st_trunc += 1;                     // pool exhausted: the row below is truncated to kw entries
@@ -173,9 +177,10 @@ ff_select_exact_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const f
 }
 
 // qlist == nullptr: every query.  Otherwise the first *qcount entries of qlist (device).
-int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, const int32_t *qlist,
+int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, const int32_t *qlist,
                         const unsigned int *qcount, int64_t max_items, cudaStream_t st) {
-    const size_t smem = (size_t)EX_WARPS * L.Dp * sizeof(float);
+    const FFSrc S = ff_src(p, L, feats, ws);
+    const size_t smem = (size_t)EX_WARPS * S.n4 * sizeof(float4);
     if (smem > 48 * 1024)
         TIMET_CUDA(cudaFuncSetAttribute(ff_select_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (max_items + EX_WARPS - 1) / EX_WARPS;
@@ -188,7 +193,7 @@ int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, c
     pool.used = reinterpret_cast<unsigned long long *>(ws + L.off_redo + FF_HDR_WIDE_USED);
     pool.cap = (unsigned long long)L.wide_cap;
     ff_select_exact_kernel<<<(int)blocks, EX_WARPS * 32, smem, st>>>(
-        p, L.N, L.Dp, L.nT, L.kw, reinterpret_cast<const float *>(ws + L.off_fn32),
+        p, L.N, S, L.nT, L.kw,
         reinterpret_cast<float *>(ws + L.off_sel_w), reinterpret_cast<int32_t *>(ws + L.off_sel_k),
         reinterpret_cast<int32_t *>(ws + L.off_sel_cnt), reinterpret_cast<unsigned long long *>(ws + L.off_stats),
         qlist, qcount, L.queries, pool);
@@ -196,8 +201,8 @@ int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, c
     return TIMET_OK;
 }
 
-int ff_select_exact_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
-    return ff_select_exact_run(p, L, ws, nullptr, nullptr, L.queries, st);
+int ff_select_exact_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st) {
+    return ff_select_exact_run(p, L, feats, ws, nullptr, nullptr, L.queries, st);
 }
 
 }  // namespace timet

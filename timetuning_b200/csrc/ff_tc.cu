@@ -308,28 +308,46 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ finalize: exact re-evaluation
-// One warp per query: lane-per-candidate canonical fp32 dot, exp, reference selection with ties.
+// One warp per query: canonical fp32 similarity of every nominated key, exp, reference selection with ties.
+//
+// The kernel is bound by dependent memory round trips per query, not by bandwidth (ncu: L2 -> SM traffic well below the
+// limit; halving the resident warps halved the speed), so the per-query chain is kept as short as possible:
+//   * the candidate list (meta word + <= 16 packed entries) of the warp's NEXT query is fetched while the current one
+//     is evaluated;
+//   * the query row is not staged through shared memory: it is loaded from global memory in the same batch as the key
+//     rows (and hits L1 when a second batch needs it again);
+//   * BATCH candidate rows are in flight together; the usual k = 5 needs ONE batch with BATCH = 6.
+// Per-candidate chains keep their i = lane, lane + 32, ... order (common.cuh), so the bits do not depend on BATCH.
 constexpr int FIN_WARPS = 8;
-constexpr int FIN_QPB = 64;                    // consecutive queries per CTA
+constexpr int FIN_QPB = 64;                    // consecutive queries per CTA (neighbouring queries nominate neighbouring keys: L1 reuse)
 
-__global__ void __launch_bounds__(FIN_WARPS * 32, 4)
-ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float *__restrict__ fn32,
+template <int BATCH, int MINB>
+__global__ void __launch_bounds__(FIN_WARPS * 32, MINB)
+ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw,
                    const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_meta,
                    float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
                    unsigned long long *__restrict__ stats, int32_t *__restrict__ redo_list,
                    unsigned int *__restrict__ redo_count, int64_t n_queries) {
-    extern __shared__ float4 qsm[];
     __shared__ unsigned long long s_stat[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
     __syncthreads();
-    float4 *qs = qsm + (size_t)warp * (Dp >> 2);
     const int W = p.grid_w;
-    unsigned long long st_sel = 0, st_ties = 0, st_trunc = 0, st_cand = 0;
-    // each CTA sweeps FIN_QPB consecutive queries (8 at a time): neighbouring queries nominate overlapping
-    // keys, so their fp32 rows are served from L1 instead of L2
-    for (int64_t qid = (int64_t)blockIdx.x * FIN_QPB + warp; qid < min(n_queries, ((int64_t)blockIdx.x + 1) * FIN_QPB); qid += FIN_WARPS) {
-        const uint32_t m0 = cand_meta[qid];
+    const int n4 = S.n4;
+    unsigned long long st_sel = 0, st_ties = 0, st_cand = 0;
+    const int64_t q_end = min(n_queries, ((int64_t)blockIdx.x + 1) * FIN_QPB);
+    int64_t qid = (int64_t)blockIdx.x * FIN_QPB + warp;
+    uint32_t m_next = 0u, c_next = 0u;
+    if (qid < q_end) {
+        m_next = __ldg(cand_meta + qid);
+        if (lane < FF_CAND_STORE) c_next = __ldg(cand + qid * FF_CAND_STORE + lane);
+    }
+    for (; qid < q_end; qid += FIN_WARPS) {
+        const uint32_t m0 = m_next, c_cur = c_next;
+        if (qid + FIN_WARPS < q_end) {                 // next query's list: in flight during this query's evaluation
+            m_next = __ldg(cand_meta + qid + FIN_WARPS);
+            if (lane < FF_CAND_STORE) c_next = __ldg(cand + (qid + FIN_WARPS) * FF_CAND_STORE + lane);
+        }
         const int nc = (int)(m0 & 0xFFFFu);
         if ((m0 & 0x10000u) != 0u) {
             if (lane == 0) redo_list[atomicAdd(redo_count, 1u)] = (int32_t)qid;
@@ -340,77 +358,77 @@ ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float
         const int tt = rem / N, i = rem - tt * N;
         const int t = p.t_begin + tt;
         const int64_t clip_row0 = (int64_t)clip * p.n_frames * N;
-        __syncwarp();
-        const float4 *qrow = reinterpret_cast<const float4 *>(fn32 + (clip_row0 + (int64_t)t * N + i) * Dp);
-        for (int d = lane; d < (Dp >> 2); d += 32) qs[d] = qrow[d];
-        __syncwarp();
+        const int64_t q_row = clip_row0 + (int64_t)t * N + i;
+        const float4 *qrow = reinterpret_cast<const float4 *>(S.x + q_row * S.ld);
         const int qr = i / W, qc = i - qr * W;
         // lane j owns candidate j (nc <= FF_CAND_STORE)
         const bool has = lane < nc;
-        int32_t key = 0, krow = 0;
+        int32_t key = 0, krow = (int32_t)q_row;
         if (has) {
-            const uint32_t code = cand[qid * FF_CAND_STORE + lane] & 0x1FFFu;
+            const uint32_t code = c_cur & 0x1FFFu;
             const int ci = (int)(code >> 10), wr = (int)((code >> 5) & 31u), wc = (int)(code & 31u);
             const int f = ctx_frame(t, p.n_last_frames, ci);
             const int j = (qr - p.radius + wr) * W + (qc - p.radius + wc);
             key = f * N + j;
             krow = (int32_t)(clip_row0 + key);
         }
-        // warp-cooperative canonical dot, four candidates at a time: all key-row loads of a chunk are in flight
-        // together (the per-candidate chains keep their i = lane, lane+32, ... order, so the bits do not change)
-        float my_sim = 0.f;
-        const int n4 = Dp >> 2;
-        for (int c0 = 0; c0 < nc; c0 += 4) {
-            const float4 *kp[4];
+        const float inv_q = __ldg(S.inv + q_row);
+        const float inv_k = __ldg(S.inv + krow);
+        // warp-cooperative canonical dot, BATCH candidates at a time: the query row and all key rows of a batch are in
+        // flight together
+        float my_dot = 0.f;
+        for (int c0 = 0; c0 < nc; c0 += BATCH) {
+            const float4 *kp[BATCH];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BATCH; ++u) {
                 const int32_t row = __shfl_sync(0xffffffffu, krow, (c0 + u < nc) ? c0 + u : c0);
-                kp[u] = reinterpret_cast<const float4 *>(fn32 + (int64_t)row * Dp);
+                kp[u] = reinterpret_cast<const float4 *>(S.x + (int64_t)row * S.ld);
             }
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int i = lane; i < n4; i += 32) {
-                const float4 x = qs[i];
-                float4 y[4];
+            float acc[BATCH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) y[u] = __ldg(kp[u] + i);
+            for (int u = 0; u < BATCH; ++u) acc[u] = 0.f;
+#pragma unroll 3
+            for (int e = lane; e < n4; e += 32) {
+                const float4 x = __ldg(qrow + e);
+                float4 y[BATCH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) acc[u] = fma4_chain(acc[u], x, y[u]);
+                for (int u = 0; u < BATCH; ++u) y[u] = __ldg(kp[u] + e);
+#pragma unroll
+                for (int u = 0; u < BATCH; ++u) acc[u] = fma4_chain(acc[u], x, y[u]);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BATCH; ++u) {
                 const float sdot = warp_sum(acc[u]);
-                if (lane == c0 + u) my_sim = sdot;
+                if (lane == c0 + u) my_dot = sdot;
             }
         }
         // canonical order (affinity desc, key asc) by counting: rank_j = #candidates that precede candidate j
-        const float my_aff = has ? affinity_from_sim(my_sim, p.temperature) : -1.f;
+        const float my_aff = has ? affinity_from_sim(sim_from_dot(my_dot, inv_q, inv_k), p.temperature) : -1.f;
         const int32_t my_key = has ? key : 0x7fffffff;
         int rank = 0;
-        for (int i = 0; i < nc; ++i) {
-            const float a = __shfl_sync(0xffffffffu, my_aff, i);
-            const int32_t kk = __shfl_sync(0xffffffffu, my_key, i);
+        for (int j = 0; j < nc; ++j) {
+            const float a = __shfl_sync(0xffffffffu, my_aff, j);
+            const int32_t kk = __shfl_sync(0xffffffffu, my_key, j);
             rank += (a > my_aff || (a == my_aff && kk < my_key)) ? 1 : 0;
         }
         TopList L;
         list_init(L);
-        for (int i = 0; i < nc; ++i) {                 // lane r picks the candidate of rank r
-            const float a = __shfl_sync(0xffffffffu, my_aff, i);
-            const int32_t kk = __shfl_sync(0xffffffffu, my_key, i);
-            const int r = __shfl_sync(0xffffffffu, rank, i);
+        for (int j = 0; j < nc; ++j) {                 // lane r picks the candidate of rank r
+            const float a = __shfl_sync(0xffffffffu, my_aff, j);
+            const int32_t kk = __shfl_sync(0xffffffffu, my_key, j);
+            const int r = __shfl_sync(0xffffffffu, rank, j);
             if (r == lane) { L.v = a; L.key = kk; }
         }
         L.cnt = nc;
         if (nc >= p.topk) L.kth = __shfl_sync(0xffffffffu, L.v, p.topk - 1);
-        const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);
-        st_sel += (unsigned long long)(m < kw ? m : kw);
+        const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);   // m <= nc <= kw
+        st_sel += (unsigned long long)m;
         st_ties += (m > p.topk);
-        st_trunc += (m > kw);
         st_cand += (unsigned long long)nc;
     }
     if (lane == 0) {
         atomicAdd(&s_stat[0], st_sel);
         atomicAdd(&s_stat[1], st_ties);
-        atomicAdd(&s_stat[2], st_trunc);
         atomicAdd(&s_stat[3], st_cand);
     }
     __syncthreads();
@@ -418,7 +436,6 @@ ff_finalize_kernel(timet_ff_params p, int N, int Dp, int nT, int kw, const float
         if (s_stat[0]) atomicAdd(&stats[1], s_stat[0]);
         if (s_stat[1]) atomicAdd(&stats[2], s_stat[1]);
         if (s_stat[3]) atomicAdd(&stats[3], s_stat[3]);
-        if (s_stat[2]) atomicAdd(&stats[5], s_stat[2]);
     }
 }
 
@@ -535,7 +552,7 @@ bool ff_tc_supported(const timet_ff_params &p) {
     return tc_geometry(p, L, &G);
 }
 
-int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, char *ws, const int32_t *qlist,
+int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, const int32_t *qlist,
                         const unsigned int *qcount, int64_t max_items, cudaStream_t st);
 
 int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
@@ -545,7 +562,7 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
 // caller can time the dominant kernel alone (bench.py roofline); set through timet_ff_select_timed
 thread_local cudaEvent_t g_ev_nominate_begin = nullptr, g_ev_nominate_end = nullptr;
 
-int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
+int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, cudaStream_t st) {
     TcGeom G;
     if (!tc_geometry(p, L, &G)) {
         set_error("tensor-core engine: unsupported shape");
@@ -582,18 +599,24 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, char *ws, c
     if (g_ev_nominate_end) TIMET_CUDA(cudaEventRecord(g_ev_nominate_end, st));
     unsigned int *redo_count = reinterpret_cast<unsigned int *>(ws + L.off_redo);
     int32_t *redo_list = reinterpret_cast<int32_t *>(ws + L.off_redo + 256);
-    const size_t fsmem = (size_t)FIN_WARPS * L.Dp * sizeof(float);
-    if (fsmem > 48 * 1024)
-        TIMET_CUDA(cudaFuncSetAttribute(ff_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    const FFSrc S = ff_src(p, L, feats, ws);
     const int64_t blocks = (L.queries + FIN_QPB - 1) / FIN_QPB;
-    ff_finalize_kernel<<<(unsigned)blocks, FIN_WARPS * 32, fsmem, st>>>(
-        p, L.N, L.Dp, L.nT, L.kw, reinterpret_cast<const float *>(ws + L.off_fn32), cand, meta,
-        reinterpret_cast<float *>(ws + L.off_sel_w), reinterpret_cast<int32_t *>(ws + L.off_sel_k),
-        reinterpret_cast<int32_t *>(ws + L.off_sel_cnt), reinterpret_cast<unsigned long long *>(ws + L.off_stats),
-        redo_list, redo_count, L.queries);
+    {
+        float *sw = reinterpret_cast<float *>(ws + L.off_sel_w);
+        int32_t *sk = reinterpret_cast<int32_t *>(ws + L.off_sel_k), *sc = reinterpret_cast<int32_t *>(ws + L.off_sel_cnt);
+        unsigned long long *stt = reinterpret_cast<unsigned long long *>(ws + L.off_stats);
+        // one batch covers the usual candidate count: k plus the odd near-tie (<= 4 for k <= 3, <= 6 for k <= 5, else 8)
+        const int fb = env_cfg().fin_batch ? env_cfg().fin_batch : (p.topk <= 3 ? 4 : (p.topk <= 5 ? 6 : 8));
+        if (fb <= 4)
+            ff_finalize_kernel<4, 4><<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(p, L.N, S, L.nT, L.kw, cand, meta, sw, sk, sc, stt, redo_list, redo_count, L.queries);
+        else if (fb <= 6)
+            ff_finalize_kernel<6, 3><<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(p, L.N, S, L.nT, L.kw, cand, meta, sw, sk, sc, stt, redo_list, redo_count, L.queries);
+        else
+            ff_finalize_kernel<8, 2><<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(p, L.N, S, L.nT, L.kw, cand, meta, sw, sk, sc, stt, redo_list, redo_count, L.queries);
+    }
     TIMET_LAUNCHED();
     // overflowed queries: exact scan (device-side count; a fixed small grid loops over the list)
-    if ((rc = ff_select_exact_run(p, L, ws, redo_list, redo_count, (int64_t)num_sms() * 8 * 8, st)) != TIMET_OK) return rc;
+    if ((rc = ff_select_exact_run(p, L, feats, ws, redo_list, redo_count, (int64_t)num_sms() * 8 * 8, st)) != TIMET_OK) return rc;
     ff_redo_count_kernel<<<1, 1, 0, st>>>(redo_count, reinterpret_cast<unsigned long long *>(ws + L.off_stats));
     TIMET_LAUNCHED();
     return TIMET_OK;

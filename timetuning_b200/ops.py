@@ -321,14 +321,23 @@ class FFPlan:
         return labels
 
     def prepare(self, feats):
+        """Stage 1.  The plan keeps a reference to `feats`: stage 2 reads the fp32 rows in place."""
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
+        self._feats = feats
         with torch.cuda.device(self.device):
             check(_cabi.lib().timet_ff_prepare(C.byref(self.params), _ptr(feats), _ptr(self.workspace), self.nbytes,
                                                _stream()), "ff_prepare")
 
+    def _prepared(self):
+        feats = getattr(self, "_feats", None)
+        if feats is None:
+            raise RuntimeError("FFPlan.select() before prepare(): the selection reads the feature rows given to prepare()")
+        return feats
+
     def select(self, engine=FF_AUTO):
         with torch.cuda.device(self.device):
-            check(_cabi.lib().timet_ff_select(C.byref(self.params), int(engine), _ptr(self.workspace), self.nbytes,
-                                              _stream()), "ff_select")
+            check(_cabi.lib().timet_ff_select(C.byref(self.params), int(engine), _ptr(self._prepared()), _ptr(self.workspace),
+                                              self.nbytes, _stream()), "ff_select")
 
     def select_timed(self, engine, ev_begin, ev_end):
         """select() with two torch.cuda.Event (either may be None) recorded by the library on the stream right before /
@@ -337,8 +346,8 @@ class FFPlan:
         hb = C.c_void_p(ev_begin.cuda_event) if ev_begin is not None else C.c_void_p(0)
         he = C.c_void_p(ev_end.cuda_event) if ev_end is not None else C.c_void_p(0)
         with torch.cuda.device(self.device):
-            check(_cabi.lib().timet_ff_select_timed(C.byref(self.params), int(engine), _ptr(self.workspace), self.nbytes,
-                                                    _stream(), hb, he), "ff_select_timed")
+            check(_cabi.lib().timet_ff_select_timed(C.byref(self.params), int(engine), _ptr(self._prepared()), _ptr(self.workspace),
+                                                    self.nbytes, _stream(), hb, he), "ff_select_timed")
 
     def gather(self, labels, hard=None):
         with torch.cuda.device(self.device):

@@ -7,7 +7,9 @@ CUDA path: the unit of work bench.py times and smoke() checks.
         -> batched Feature-Forwarding of Q_source over every clip
         -> (Q_source, Q_target, last-frame hard labels)
 
-Stream choreography (StepRunner, overlap=True).  The Sinkhorn chain does not depend on the affinity / top-k selection
+Stream choreography (StepRunner, overlap=True; OFF by default -- measured on a B200 it does not pay: the finalize and
+gather kernels are bound by resident warps x loads in flight, and every warp slot / register the co-resident Sinkhorn
+kernel takes slows them by as much as the overlap hides, profiles/r2_experiments.md).  The Sinkhorn chain does not depend on the affinity / top-k selection
 and vice versa; only the label gather needs Q_source.  So the chain runs on a second, high-priority stream:
 
     main : prepare -> select (tcgen05 kernel, finalize) ------------------> [wait Q_source] -> gather
@@ -57,7 +59,7 @@ class StepRunner:
     """Device-resident FF + Sinkhorn step with its buffers, plan and streams kept across calls."""
 
     def __init__(self, bs, fs, sr, D, dh, K, n_last_frames=7, size_mask_neighborhood=6, topk=5, epsilon=0.05,
-                 sinkhorn_iterations=10, world_size=1, engine=ops.FF_AUTO, overlap=True, device=None):
+                 sinkhorn_iterations=10, world_size=1, engine=ops.FF_AUTO, overlap=False, device=None):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.bs, self.fs, self.sr, self.N, self.D, self.dh, self.K = bs, fs, sr, sr * sr, D, dh, K
         self.eps, self.iters, self.world_size, self.engine = float(epsilon), int(sinkhorn_iterations), int(world_size), engine
