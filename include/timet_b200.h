@@ -85,6 +85,13 @@ typedef struct timet_sinkhorn_opts {
 int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
                       timet_comm_t comm, float *q_out, const timet_sinkhorn_opts *opts, void *workspace,
                       size_t workspace_bytes, timet_stream_t stream);
+/* Two problems of the same shape (B, K, kind, eps, iters) in ONE resident launch: the source and the target assignment
+ * of a training step (time_tuning.py:268,275).  While one problem waits for its grid-wide marginal reduction the CTAs
+ * sweep the other; results are bit-identical to two timet_sinkhorn_ex calls.  workspace: 2 x
+ * timet_sinkhorn_workspace_bytes(B, K).  Falls back to two sequential calls when the pair does not fit the SMs. */
+int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, int input_kind, float epsilon, int iters,
+                        int world_size, timet_comm_t comm, float *q0, const timet_sinkhorn_opts *opts0, float *q1,
+                        const timet_sinkhorn_opts *opts1, void *workspace, size_t workspace_bytes, timet_stream_t stream);
 /* 1 if a call of this shape runs as ONE resident kernel (rows of exp(S/eps) fit the SMs' shared memory), 0 if it runs
  * as one streaming pass per iteration */
 int timet_sinkhorn_resident(int64_t B, int K);

@@ -384,3 +384,103 @@ def test_sinkhorn_rows_beyond_shared_memory():
     assert ref.shape == (2048, K)
     full = O.sinkhorn_scaling(scores, 0.05, 10, dtype=np.float64)
     assert_close(q, full, what="B=100352 vs fp64 oracle")
+
+
+@pytest.mark.parametrize("B,K,iters", [(32 * 784, 200, 10), (8 * 784, 200, 3), (4 * 196, 64, 1), (2 * 3136, 300, 10), (1000, 516, 4)])
+def test_sinkhorn_pair_is_two_single_calls(B, K, iters):
+    """timet_sinkhorn_pair (two problems, one resident launch, reductions overlapped) returns the bits of two single
+    calls -- resident pair where it fits, sequential fallback otherwise (K = 516)."""
+    s0, s1 = cu(synth.cosine_scores(B, K, seed=5)), cu(synth.cosine_scores(B, K, seed=6))
+    q0, q1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
+    r0, r1 = tb.sinkhorn_from_scores(s0, 0.05, iters), tb.sinkhorn_from_scores(s1, 0.05, iters)
+    assert torch.equal(q0, r0) and torch.equal(q1, r1), ((q0 - r0).abs().max().item(), (q1 - r1).abs().max().item())
+    assert_close(q1.cpu().numpy(), O.sinkhorn_scaling(s1.cpu().numpy(), 0.05, iters, dtype=np.float64), what="pair vs fp64 oracle")
+
+
+def test_sinkhorn_strided_output_into_label_frames():
+    """out=labels[:, 0]: the assignment of clip b lands in frame 0 of the channel-last label tensor (no copy between
+    Sinkhorn and Feature-Forwarding, time_tuning.py:144-147)."""
+    bs, fs, N, K = 6, 3, 196, 200
+    s0, s1 = cu(synth.cosine_scores(bs * N, K, seed=7)), cu(synth.cosine_scores(bs * N, K, seed=8))
+    labels = torch.full((bs, fs, N, K), -1.0, device="cuda")
+    flat = torch.empty((bs, N, K), device="cuda")
+    tb.sinkhorn_pair_from_scores(s0, s1, 0.05, 10, out0=labels[:, 0], out1=flat)
+    assert torch.equal(labels[:, 0].reshape(bs * N, K), tb.sinkhorn_from_scores(s0, 0.05, 10))
+    assert torch.equal(flat.reshape(bs * N, K), tb.sinkhorn_from_scores(s1, 0.05, 10))
+    assert (labels[:, 1:] == -1).all(), "other frames untouched"
+    lab2 = torch.full((bs, fs, N, K), -1.0, device="cuda")
+    tb.sinkhorn_from_scores(s0, 0.05, 10, out=lab2[:, 0])
+    assert torch.equal(lab2, labels)
+    with pytest.raises(ValueError):
+        tb.sinkhorn_from_scores(s0, 0.05, 10, out=labels[:, 0, :, :100])
+
+
+def test_sinkhorn_share_sm_variant_matches():
+    """The 512-thread resident variant (leaves half the SM to co-resident kernels) against the default and the oracle."""
+    s0 = cu(synth.cosine_scores(8 * 784, 200, seed=9))
+    a, b = tb.sinkhorn_from_scores(s0, 0.05, 10), tb.sinkhorn_from_scores(s0, 0.05, 10, share_sm=True)
+    assert_close(b.cpu().numpy(), a.cpu().numpy(), atol=1e-7, rtol=1e-5, what="share_sm vs default")
+
+
+def test_cosine_scores_multi_and_autograd():
+    """One GEMM launch for several feature blocks == separate calls; the autograd wrapper's gradients == torch's."""
+    from timetuning_b200 import training
+    rng = np.random.default_rng(0)
+    xs = [cu((rng.standard_normal((1568, 256)) * 3).astype(np.float32)) for _ in range(3)]
+    p = cu(synth.prototypes(200, 256, seed=1))
+    multi = tb.cosine_scores_multi(xs, p)
+    for i, x in enumerate(xs):
+        assert torch.equal(multi[i * 1568:(i + 1) * 1568], tb.cosine_scores(x, p))
+    x = xs[0].clone().requires_grad_(True)
+    pp = p.clone().requires_grad_(True)
+    g = cu(rng.standard_normal((1568, 200)).astype(np.float32))
+    (training.cosine_scores_autograd(x, pp) * g).sum().backward()
+    x2 = xs[0].clone().requires_grad_(True)
+    p2 = p.clone().requires_grad_(True)
+    ((torch.nn.functional.normalize(x2, dim=-1) @ p2.t()) * g).sum().backward()
+    assert_close(x.grad.cpu().numpy(), x2.grad.cpu().numpy(), atol=1e-5, rtol=1e-4, what="d/dx")
+    assert_close(pp.grad.cpu().numpy(), p2.grad.cpu().numpy(), atol=1e-4, rtol=1e-4, what="d/dprototypes")
+
+
+def test_non_square_grid_drop_ins():
+    """Python drop-ins with a (h, w) spatial_resolution (additive; DAVIS 480x854 style) against a dense fp64 restatement."""
+    H, W, D, C, fs, radius, topk = 9, 16, 48, 5, 4, 3, 4
+    N = H * W
+    feats = synth.clip_features(1, fs, 16, D, seed=13)[0][:, :N]        # any [fs, N, D] features
+    first = synth.soft_labels(N, C, seed=2).T.reshape(1, C, H, W)
+
+    class FEhw:
+        spatial_resolution = (H, W)
+    out = torch.stack(tb.propagate_labels(7, radius, topk, FEhw(), cu(feats), cu(first), True)).cpu().numpy()
+    fn = O.l2_normalize_rows(feats).astype(np.float64)
+    rows, cols = np.arange(N) // W, np.arange(N) % W
+    win = (np.abs(rows[:, None] - rows[None]) <= radius) & (np.abs(cols[:, None] - cols[None]) <= radius)
+    segs = [first[0].reshape(C, N).T.astype(np.float64)]
+    for t in range(1, fs):
+        ctx = O.context_frames(t, 7)
+        aff = np.concatenate([np.exp(fn[t] @ fn[c].T / 0.1) * win for c in ctx], axis=1)
+        kth = np.sort(aff, axis=1)[:, -topk]
+        wgt = np.where(aff >= kth[:, None], aff, 0)
+        wgt /= wgt.sum(1, keepdims=True)
+        segs.append(wgt @ np.concatenate([segs[c] for c in ctx], axis=0))
+    want = np.stack([s.T.reshape(C, H, W) for s in segs[1:]])
+    assert out.shape == want.shape and np.abs(out - want).max() < 1e-5
+    assert np.array_equal(tb.restrict_neighborhood(H, W, radius).cpu().numpy(), O.restrict_neighborhood(H, W, radius))
+    pred = tb.propagate_labels_eval(7, radius, topk, cu(feats), cu(first), (4 * H, 4 * W), grid=(H, W))
+    assert tuple(pred.shape) == (fs - 1, 4 * H, 4 * W)
+
+
+def test_exact_engine_vs_oracle_config5_grid():
+    """BASELINE configs[4] grid (56 x 56 patches, D = 768) through the EXACT engine against the oracle itself (the
+    tensor-core engine is checked against the exact one elsewhere): one clip, three frames."""
+    sr, D, C, fs = 56, 768, 12, 3
+    N = sr * sr
+    feats = synth.clip_features(1, fs, sr, D, seed=21)
+    first = synth.soft_labels(N, C, seed=22)[None]
+    for engine in (tb.FF_EXACT, tb.FF_AUTO):
+        labels, hard = tb.propagate_labels_batched(cu(feats), cu(first), 7, 6, 5, engine=engine, check=True)
+        ref = _oracle_clip(feats[0], first[0], 7, 6, 5, sr)
+        _, taint, _ = ff_taint(7, 6, 5, sr, feats[0], first[0].T.reshape(C, sr, sr))
+        got = labels[0, 1:].permute(0, 2, 1).reshape(fs - 1, C, sr, sr).cpu().numpy()
+        check_soft(got, ref, taint, what=f"56x56x768 engine {engine}")
+        check_hard(hard[0].cpu().numpy(), ref[-1], taint[-1], what="56x56x768 hard")

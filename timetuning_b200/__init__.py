@@ -5,9 +5,10 @@ sm_100a CUDA (csrc/) behind a C ABI (include/timet_b200.h) and the Python mirror
 callables (ops.py).  `install()` binds them over the reference's module attributes.
 """
 from .ops import (FFPlan, FF_AUTO, FF_EXACT, FF_TC, cosine_scores, label_propagation, norm_mask, propagate_labels,  # noqa: F401
-                  propagate_labels_batched, propagate_labels_eval, upsample_argmax, restrict_neighborhood, sinkhorn, sinkhorn_from_scores)
+                  propagate_labels_batched, propagate_labels_eval, upsample_argmax, restrict_neighborhood, sinkhorn, sinkhorn_from_scores,
+                  sinkhorn_pair_from_scores, cosine_scores_multi)
 
-__all__ = ["sinkhorn", "sinkhorn_from_scores", "cosine_scores", "restrict_neighborhood", "norm_mask", "label_propagation",
+__all__ = ["sinkhorn", "sinkhorn_from_scores", "sinkhorn_pair_from_scores", "cosine_scores_multi", "cosine_scores", "restrict_neighborhood", "norm_mask", "label_propagation",
            "propagate_labels", "propagate_labels_batched", "propagate_labels_eval", "upsample_argmax", "FFPlan", "FF_AUTO", "FF_EXACT", "FF_TC", "install", "Installation"]
 
 

@@ -48,9 +48,11 @@ void env_reload() {
     e.tc_dyn = env_int("TIMET_TC_DYN", 1) != 0;
     e.tc_trace = env_int("TIMET_TC_TRACE", 0) == 1;
     e.sk_streaming = env_int("TIMET_SK_STREAMING", 0) == 1;
+    e.sk_no_pair = env_int("TIMET_SK_PAIR", 1) == 0;
     e.sk_ustride = env_int("TIMET_SK_USTRIDE", 0);
     e.fin_batch = env_int("TIMET_FIN_BATCH", 0);
     e.gather_batch = env_int("TIMET_GATHER_BATCH", 0);
+    e.sc_stages = env_int("TIMET_SC_STAGES", 0);
     const char *to = getenv("TIMET_P2P_TIMEOUT_S");
     e.p2p_timeout_s = (to && atof(to) > 0.0) ? atof(to) : 600.0;    // NCCL-like patience: rank skew of minutes is legal
     g_env = e;

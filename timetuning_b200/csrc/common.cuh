@@ -49,8 +49,9 @@ int num_sms();
 struct EnvCfg {
     int tc_pflags, tc_flags, tc_stages, tc_nbuf, tc_clip_group;   // 0 = default
     bool tc_pair, tc_persist, tc_dyn, tc_trace;
-    bool sk_streaming;
+    bool sk_streaming, sk_no_pair;
     int sk_ustride;                                                // 0 = default
+    int sc_stages;                                                 // cosine-scores GEMM ring depth (2 = two CTAs per SM, default; 4)
     int gather_batch;                                              // gather: label rows in flight per batch (0 = by topk)
     int fin_batch;                                                 // finalize: candidate rows in flight per batch (0 = by topk)
     double p2p_timeout_s;                                          // peer-exchange / marginal wait time-out (seconds)

@@ -15,7 +15,9 @@
 namespace timet {
 
 constexpr int SC_THREADS = 192;       // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 epilogue
-constexpr int SC_STAGES = 4;
+constexpr int SC_MAX_STAGES = 4;
+// Ring depth 2 (85 KB per CTA at K = 200) lets TWO CTAs share an SM: one CTA's epilogue (TMEM -> shared -> global) and
+// prologue run under the other's TMA / MMA main loop; depth 4 = one CTA per SM, everything in sequence (round 1).
 
 constexpr int SC_MAX_INPUTS = 4;
 struct ScInputs {
@@ -46,11 +48,12 @@ scores_prep_kernel(ScInputs in, __half *__restrict__ out, int64_t rows, int dh, 
 }
 
 struct __align__(8) ScCtl {
-    uint64_t full[SC_STAGES], empty[SC_STAGES], tmem_full;
+    uint64_t full[SC_MAX_STAGES], empty[SC_MAX_STAGES], tmem_full;
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(SC_THREADS, 1)
+template <int SC_STAGES>
+__global__ void __launch_bounds__(SC_THREADS, SC_STAGES <= 2 ? 2 : 1)
 scores_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    float *__restrict__ out, int64_t rows, int K, int Np, int dhp) {
     extern __shared__ uint8_t smem_raw[];
@@ -207,10 +210,16 @@ int timet_cosine_scores_multi(const float *const *x_list, int n_x, int64_t rows_
         if ((rc = tc_make_map(&map_a, a2, B + 128, 2 * dhp, 128)) != TIMET_OK) return rc;
         if ((rc = tc_make_map(&map_b, b2, Kp, 2 * dhp, Np)) != TIMET_OK) return rc;
     }
-    const size_t smem = 1024 + (size_t)SC_STAGES * (128 * 128 + (size_t)Np * 128) + sizeof(ScCtl) + 4 * 32 * 33 * sizeof(float) + 64;
-    TIMET_CUDA(cudaFuncSetAttribute(scores_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int stages = env_cfg().sc_stages == 4 ? 4 : 2;
+    const size_t smem = 1024 + (size_t)stages * (128 * 128 + (size_t)Np * 128) + sizeof(ScCtl) + 4 * 32 * 33 * sizeof(float) + 64;
     dim3 grid((unsigned)((B + 127) / 128), (unsigned)n_tiles);
-    scores_gemm_kernel<<<grid, SC_THREADS, smem, st>>>(map_a, map_b, scores_out, B, K, Np, dhp);
+    if (stages == 4) {
+        TIMET_CUDA(cudaFuncSetAttribute(scores_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scores_gemm_kernel<4><<<grid, SC_THREADS, smem, st>>>(map_a, map_b, scores_out, B, K, Np, dhp);
+    } else {
+        TIMET_CUDA(cudaFuncSetAttribute(scores_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        scores_gemm_kernel<2><<<grid, SC_THREADS, smem, st>>>(map_a, map_b, scores_out, B, K, Np, dhp);
+    }
     TIMET_LAUNCHED();
     return TIMET_OK;
 }

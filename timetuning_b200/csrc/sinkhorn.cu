@@ -532,6 +532,243 @@ __global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PAIR variant: TWO Sinkhorn problems of the same shape in ONE resident launch (the source and the target assignment of a
+// training step, time_tuning.py:268,275).  A single call spends more than half of every iteration waiting for its
+// grid-wide reduction (atomic -> L2 -> poll) -- with two independent problems in one kernel each CTA sweeps one problem
+// while the other's reduction is in flight:
+//     S(A,0) P(A,0) | S(B,it) P(B,it)  W(A,it)  S(A,it+1) P(A,it+1)  W(B,it) | ...        S sweep, P post, W wait + update
+// Problem A keeps exp(S/eps) resident in shared memory like sk_resident; both do not fit (2 x 136 KB at config 2), so
+// problem B's rows are re-read from L2 (the 20 MB score matrix stays L2-resident) and re-exponentiated every iteration
+// -- bit-identical values, and the extra L2 traffic rides under A's reduction latency.  The arithmetic per problem is
+// the one of sk_resident<.., 1024> in the same order, so a pair call returns the same bits as two single calls.
+struct SkPairArgs {
+    SkResArgs a[2];           // per-problem pointers / accumulators (shape fields equal); a[0] is the resident one
+};
+
+template <int NV4, int WARPS, bool RESIDENT>
+__device__ __forceinline__ void skp_sweep(const SkResArgs &A, const float4 *E, int64_t row0, int nrows, const float *a_s,
+                                          float4 (&acc)[NV4], bool last, int warp, int lane) {
+    const int K = A.K, K4 = K >> 2;
+    float4 av[NV4];
+#pragma unroll
+    for (int v = 0; v < NV4; ++v) {
+        const int i4 = lane + 32 * v;
+        av[v] = (i4 < K4) ? reinterpret_cast<const float4 *>(a_s)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    constexpr int RPW = (NV4 <= 2) ? 2 : 1;
+    for (int rl = warp; rl < nrows; rl += RPW * WARPS) {
+        const int rl2 = rl + WARPS;
+        const bool two = RPW == 2 && rl2 < nrows;
+        float4 p[NV4], q[NV4];
+        float s = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f), f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RESIDENT) {
+                if (i4 < K4) e = E[(size_t)rl * K4 + i4];
+                if (two && i4 < K4) f = E[(size_t)rl2 * K4 + i4];
+            } else {
+                if (i4 < K4) e = __ldg(reinterpret_cast<const float4 *>(A.in + (row0 + rl) * K) + i4);
+                if (two && i4 < K4) f = __ldg(reinterpret_cast<const float4 *>(A.in + (row0 + rl2) * K) + i4);
+                if (A.scores_mode) {
+                    if (i4 < K4) {
+                        e.x = expf(e.x * A.inv_eps); e.y = expf(e.y * A.inv_eps); e.z = expf(e.z * A.inv_eps); e.w = expf(e.w * A.inv_eps);
+                    }
+                    if (two && i4 < K4) {
+                        f.x = expf(f.x * A.inv_eps); f.y = expf(f.y * A.inv_eps); f.z = expf(f.z * A.inv_eps); f.w = expf(f.w * A.inv_eps);
+                    }
+                }
+            }
+            p[v] = make_float4(e.x * av[v].x, e.y * av[v].y, e.z * av[v].z, e.w * av[v].w);
+            q[v] = make_float4(f.x * av[v].x, f.y * av[v].y, f.z * av[v].z, f.w * av[v].w);
+            s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
+            s2 += (q[v].x + q[v].y) + (q[v].z + q[v].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (!last) {
+            const float b = __fdiv_rn(A.c, s);
+            const float b2 = two ? __fdiv_rn(A.c, s2) : 0.f;
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                acc[v].x = fmaf(p[v].x, b, acc[v].x); acc[v].y = fmaf(p[v].y, b, acc[v].y);
+                acc[v].z = fmaf(p[v].z, b, acc[v].z); acc[v].w = fmaf(p[v].w, b, acc[v].w);
+            }
+            if (two) {
+#pragma unroll
+                for (int v = 0; v < NV4; ++v) {
+                    acc[v].x = fmaf(q[v].x, b2, acc[v].x); acc[v].y = fmaf(q[v].y, b2, acc[v].y);
+                    acc[v].z = fmaf(q[v].z, b2, acc[v].z); acc[v].w = fmaf(q[v].w, b2, acc[v].w);
+                }
+            }
+        } else {
+            const float inv = __fdiv_rn(1.f, s);
+            const float inv2 = two ? __fdiv_rn(1.f, s2) : 0.f;
+            float4 *dst = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + rl, K, A.out_block_rows, A.out_block_stride));
+            float4 *dst2 = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + (two ? rl2 : rl), K, A.out_block_rows, A.out_block_stride));
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                const int i4 = lane + 32 * v;
+                if (i4 < K4) __stcs(dst + i4, make_float4(p[v].x * inv, p[v].y * inv, p[v].z * inv, p[v].w * inv));
+                if (two && i4 < K4) __stcs(dst2 + i4, make_float4(q[v].x * inv2, q[v].y * inv2, q[v].z * inv2, q[v].w * inv2));
+            }
+        }
+    }
+}
+
+// P: fold the CTA's marginal partials and add them (with the arrival) to the grid-wide fixed-point accumulators
+template <int NV4, int WARPS>
+__device__ __forceinline__ void skp_post(const SkResArgs &A, int it, float *red, const float4 (&acc)[NV4], int warp, int lane) {
+    const int K = A.K, K4 = K >> 2;
+    skr_fold_warps<NV4, WARPS>(red, acc, K, K4, warp, lane);
+    const int i = threadIdx.x;
+    if (i < K) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
+        unsigned long long *acc_i = A.ufix + (size_t)(it & 1) * K * A.ustride + (size_t)i * A.ustride;
+        atomicAdd(acc_i, ((unsigned long long)__float2ll_rn(t * A.ufix_scale) << SKR_CNT_BITS) + 1ull);
+    }
+    __syncthreads();                                       // the fold scratch is free again
+}
+
+// W: wait until every CTA's contribution of iteration `it` is in, (multi-GPU: exchange the K-vector with the peers,)
+// and apply Q *= r / u to the scaling vector (my_utils.py:268)
+template <int THREADS>
+__device__ __forceinline__ void skp_wait(const SkResArgs &A, int it, unsigned long long &prev0, unsigned long long &prev1,
+                                         unsigned long long &xch, float *a_s, float *u_s) {
+    const int K = A.K;
+    const int i = threadIdx.x;
+    if (i < K) {
+        unsigned long long *acc_i = A.ufix + (size_t)(it & 1) * K * A.ustride + (size_t)i * A.ustride;
+        const unsigned long long want = (unsigned long long)((it >> 1) + 1) * gridDim.x;
+        unsigned long long v, t0 = 0ull;
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(acc_i) : "memory");
+            if ((v & ((1ull << SKR_CNT_BITS) - 1ull)) >= want) break;
+            if ((++spins & 0xFFFFu) == 0u) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0ull) t0 = now;
+                else if (now - t0 > A.timeout_ns) {
+                    printf("timet: sinkhorn (pair) marginal wait timed out (block %d column %d iteration %d)\n", (int)blockIdx.x, i, it);
+                    __trap();
+                }
+            }
+        } while (true);
+        const unsigned long long cur = v >> SKR_CNT_BITS;
+        const unsigned long long prev = (it & 1) ? prev1 : prev0;
+        u_s[i] = (float)((double)(long long)(cur - prev) * (double)A.ufix_inv);
+        if (it & 1) prev1 = cur; else prev0 = cur;
+    }
+    __syncthreads();
+    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, u_s);
+    if (i < K) a_s[i] = a_s[i] * __fdiv_rn(A.r, u_s[i]);
+    __syncthreads();
+}
+
+template <int NV4>
+__global__ void __launch_bounds__(1024, 1) sk_resident_pair(SkPairArgs P) {
+    constexpr int THREADS = 1024, WARPS = THREADS / 32;
+    extern __shared__ float4 smem4[];
+    const SkResArgs &A = P.a[0], &Bp = P.a[1];
+    const int K = A.K, K4 = K >> 2;
+    float4 *E = smem4;                                                              // [rows_per_cta, K4]: problem A
+    float *a_sA = reinterpret_cast<float *>(smem4 + (size_t)A.rows_per_cta * K4);   // [K]
+    float *a_sB = a_sA + K;                                                         // [K]
+    float *u_s = a_sB + K;                                                          // [K]
+    float *red = u_s + K;                                                           // [SKR_RED, K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_cta;
+    const int nrows = (int)max((int64_t)0, min((int64_t)A.rows_per_cta, A.B - row0));
+
+    float4 acc[NV4];
+    // ---- pass 0 of both problems: column sums of E (A: exponentiate once into shared memory; B: streamed)
+    for (int c = 0; c < 2; ++c) {
+        const SkResArgs &X = P.a[c];
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int rl = warp; rl < nrows; rl += WARPS) {
+            const float4 *src = reinterpret_cast<const float4 *>(X.in + (row0 + rl) * K);
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                const int i4 = lane + 32 * v;
+                if (i4 < K4) {
+                    float4 e = __ldg(src + i4);
+                    if (X.scores_mode) {
+                        e.x = expf(e.x * X.inv_eps); e.y = expf(e.y * X.inv_eps);
+                        e.z = expf(e.z * X.inv_eps); e.w = expf(e.w * X.inv_eps);
+                    }
+                    if (c == 0) E[(size_t)rl * K4 + i4] = e;
+                    acc[v].x += e.x; acc[v].y += e.y; acc[v].z += e.z; acc[v].w += e.w;
+                }
+            }
+        }
+        skr_fold_warps<NV4, WARPS>(red, acc, K, K4, warp, lane);
+        for (int i = threadIdx.x; i < K; i += THREADS) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
+            X.partials[(size_t)blockIdx.x * K + i] = t;
+        }
+        __syncthreads();
+    }
+    grid_barrier(A.bar, gridDim.x);
+    unsigned long long xch = A.epoch0;
+    fold_partials<THREADS>(A.partials, gridDim.x, K, red, a_sA, 0.f);
+    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_sA);
+    fold_partials<THREADS>(Bp.partials, gridDim.x, K, red, a_sB, 0.f);
+    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_sB);
+    for (int i = threadIdx.x; i < K; i += THREADS) {
+        a_sA[i] = __fdiv_rn(A.r, a_sA[i]);
+        a_sB[i] = __fdiv_rn(A.r, a_sB[i]);
+    }
+    __syncthreads();
+
+    // ---- iterations, software-pipelined across the two problems
+    unsigned long long pA0 = 0ull, pA1 = 0ull, pB0 = 0ull, pB1 = 0ull;
+    const int n = A.iters;
+    skp_sweep<NV4, WARPS, true>(A, E, row0, nrows, a_sA, acc, n == 1, warp, lane);
+    if (n > 1) skp_post<NV4, WARPS>(A, 0, red, acc, warp, lane);
+    for (int it = 0; it < n; ++it) {
+        const bool last = (it == n - 1);
+        skp_sweep<NV4, WARPS, false>(Bp, nullptr, row0, nrows, a_sB, acc, last, warp, lane);
+        if (last) break;
+        skp_post<NV4, WARPS>(Bp, it, red, acc, warp, lane);
+        skp_wait<THREADS>(A, it, pA0, pA1, xch, a_sA, u_s);
+        skp_sweep<NV4, WARPS, true>(A, E, row0, nrows, a_sA, acc, it + 1 == n - 1, warp, lane);
+        if (it + 1 < n - 1) skp_post<NV4, WARPS>(A, it + 1, red, acc, warp, lane);
+        skp_wait<THREADS>(Bp, it, pB0, pB1, xch, a_sB, u_s);
+    }
+}
+
+static bool sk_pair_plan(int64_t B, int K, int *grid, int *rows_per_cta, size_t *smem) {
+    if (K % 4 != 0 || K > 128 * 3) return false;          // NV4 <= 3
+    const int g = num_sms();
+    const int64_t rpc = (B + g - 1) / g;
+    const size_t need = (size_t)rpc * K * 4 + (size_t)3 * K * 4 + (size_t)SKR_RED * K * 4;
+    if (need > 226 * 1024) return false;
+    *grid = (int)((B + rpc - 1) / rpc);
+    *rows_per_cta = (int)rpc;
+    *smem = need;
+    return true;
+}
+
+template <int NV4>
+static int sk_pair_launch(SkPairArgs &P, int grid, size_t smem, cudaStream_t st) {
+    TIMET_CUDA(cudaFuncSetAttribute(sk_resident_pair<NV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {&P};
+    TIMET_CUDA(cudaLaunchCooperativeKernel((const void *)sk_resident_pair<NV4>, dim3(grid), dim3(1024), args, smem, st));
+    launch_counter()++;
+    return TIMET_OK;
+}
+
 static bool sk_resident_plan(int64_t B, int K, int *grid, int *rows_per_cta, size_t *smem) {
     if (K % 4 != 0 || K > 128 * SK_MAX_V4) return false;
     const int g = num_sms();
@@ -716,6 +953,73 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
     }
     A.R_prev = Rbuf[(iters - 1) & 1]; A.R = nullptr;
     return sk_launch<2>(A, grid, st);
+}
+
+
+int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, int input_kind, float epsilon, int iters,
+                        int world_size, timet_comm_t comm, float *q0, const timet_sinkhorn_opts *opts0, float *q1,
+                        const timet_sinkhorn_opts *opts1, void *workspace, size_t workspace_bytes, timet_stream_t stream) {
+    TIMET_CHECK_ARG(in0 && in1 && q0 && q1 && workspace, "sinkhorn_pair: NULL pointer");
+    TIMET_CHECK_ARG(B >= 1 && K >= 1, "sinkhorn_pair: bad shape B=%lld K=%d", (long long)B, K);
+    const size_t one = timet_sinkhorn_workspace_bytes(B, K);
+    if (workspace_bytes < 2 * one) {
+        set_error("sinkhorn_pair: workspace %zu < %zu bytes (2 x timet_sinkhorn_workspace_bytes)", workspace_bytes, 2 * one);
+        return TIMET_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *in[2] = {in0, in1};
+    float *qo[2] = {q0, q1};
+    const timet_sinkhorn_opts *op[2] = {opts0, opts1};
+    char *wsp[2] = {(char *)workspace, (char *)workspace + one};
+    const EnvCfg &E = env_cfg();
+    int rgrid, rpc;
+    size_t rsmem;
+    void **peers = nullptr;
+    int prank = 0, pws = 1;
+    unsigned long long *pepoch = nullptr;
+    const bool p2p = world_size > 1 && comm != nullptr && comm_p2p_info(comm, &peers, &prank, &pws, &pepoch) && pws == world_size && K <= P2P_MAX_K;
+    bool ok = (world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && !E.sk_no_pair && epsilon > 0.f &&
+              (input_kind == TIMET_SK_EXP || input_kind == TIMET_SK_SCORES) && sk_pair_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160 &&
+              (int64_t)(iters / 2 + 1) * rgrid < (1 << SKR_CNT_BITS);
+    for (int c = 0; c < 2 && ok; ++c) {
+        const int64_t obr = op[c] ? op[c]->out_block_rows : 0, obs = op[c] ? op[c]->out_block_stride : 0;
+        ok = (reinterpret_cast<uintptr_t>(in[c]) & 15) == 0 && (reinterpret_cast<uintptr_t>(qo[c]) & 15) == 0 && (obs % 4) == 0 &&
+             (obr <= 0 || (obs >= obr * K && B % obr == 0));
+    }
+    if (!ok) {      // not a resident pair: two independent calls (each validates its own arguments)
+        int rc = timet_sinkhorn_ex(in0, B, K, input_kind, epsilon, iters, world_size, comm, q0, opts0, wsp[0], one, stream);
+        if (rc != TIMET_OK) return rc;
+        return timet_sinkhorn_ex(in1, B, K, input_kind, epsilon, iters, world_size, comm, q1, opts1, wsp[1], one, stream);
+    }
+    SkPairArgs P;
+    const size_t bar_off = (size_t)322 * K * sizeof(float);
+    const size_t ufix_off = align_up(bar_off + 64, 256);
+    const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;
+    int head = 1;
+    while ((1 << head) < iters / 2 + 2) ++head;
+    for (int c = 0; c < 2; ++c) {
+        TIMET_CUDA(cudaMemsetAsync(wsp[c] + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
+        SkResArgs &R = P.a[c];
+        R.ustride = ustride;
+        R.ufix_scale = ldexpf(1.0f, 47 - head);
+        R.ufix_inv = ldexpf(1.0f, head - 47);
+        R.ufix = (unsigned long long *)(wsp[c] + ufix_off);
+        R.out_block_rows = op[c] ? op[c]->out_block_rows : 0;
+        R.out_block_stride = op[c] ? op[c]->out_block_stride : 0;
+        R.in = in[c]; R.q_out = qo[c]; R.partials = (float *)wsp[c]; R.bar = (unsigned int *)(wsp[0] + bar_off);
+        R.B = B; R.K = K; R.iters = iters; R.rows_per_cta = rpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
+        R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
+        R.r = 1.0f / (float)K; R.c = 1.0f / ((float)B * (float)world_size);
+        R.peers = p2p ? peers : nullptr; R.rank = prank; R.ws = p2p ? pws : 1;
+        R.epoch0 = p2p ? *pepoch : 0ull;
+        R.timeout_ns = (unsigned long long)(E.p2p_timeout_s * 1e9);
+    }
+    if (p2p) *pepoch += 2ull * (unsigned long long)iters;      // per problem: pass 0 + (iters - 1) iterations
+    switch ((K / 4 + 31) / 32) {
+        case 1: return sk_pair_launch<1>(P, rgrid, rsmem, st);
+        case 2: return sk_pair_launch<2>(P, rgrid, rsmem, st);
+        default: return sk_pair_launch<3>(P, rgrid, rsmem, st);
+    }
 }
 
 }

@@ -97,6 +97,43 @@ def sinkhorn_from_scores(scores: torch.Tensor, epsilon: float, nmb_iters: int, w
     return res if dev_in.type == "cuda" else res.to(dev_in)
 
 
+@torch.no_grad()
+def sinkhorn_pair_from_scores(scores0, scores1, epsilon: float, nmb_iters: int, world_size: int = 1, out0=None, out1=None):
+    """Two find_optimal_assignment calls of the same shape in ONE resident launch (the source and target assignment of a
+    training step, time_tuning.py:268,275): the kernel sweeps one problem while the other waits for its grid-wide marginal
+    reduction.  Bit-identical to two sinkhorn_from_scores calls.  scores0/1 [B, K] CUDA float32 -> (Q0, Q1); out0 / out1
+    as in sinkhorn_from_scores."""
+    S = [_to_cuda(x.detach()).float().contiguous() for x in (scores0, scores1)]
+    if S[0].dim() != 2 or S[0].shape != S[1].shape:
+        raise ValueError(f"two score matrices of the same shape [B, K] expected, got {tuple(S[0].shape)} and {tuple(S[1].shape)}")
+    lib = _cabi.lib()
+    B, K = S[0].shape
+    comm = None
+    if world_size > 1:
+        if _comm["handle"] is None or _comm["world_size"] != world_size:
+            raise RuntimeError(f"sinkhorn(world_size={world_size}) needs timetuning_b200.dist.init_comm() first")
+        comm = _comm["handle"]
+    outs, opts = [], []
+    with torch.cuda.device(S[0].device):
+        for o in (out0, out1):
+            opt = SinkhornOpts(0, 0, 0, 0)
+            if o is None:
+                o = torch.empty((B, K), dtype=torch.float32, device=S[0].device)
+            else:
+                if not (o.is_cuda and o.dtype == torch.float32 and o.dim() == 3 and o.shape[2] == K and o.stride(2) == 1
+                        and o.stride(1) == K and o.shape[0] * o.shape[1] == B):
+                    raise ValueError(f"out must be CUDA float32 [n_blocks, block_rows, {K}] covering {B} rows, got {tuple(o.shape)}")
+                opt.out_block_rows, opt.out_block_stride = o.shape[1], o.stride(0)
+            outs.append(o)
+            opts.append(opt)
+        nbytes = 2 * int(lib.timet_sinkhorn_workspace_bytes(B, K))
+        ws = _workspace(nbytes, S[0].device)
+        check(lib.timet_sinkhorn_pair(_ptr(S[0]), _ptr(S[1]), B, K, SK_SCORES, float(epsilon), int(nmb_iters), int(world_size), comm,
+                                      _ptr(outs[0]), C.byref(opts[0]), _ptr(outs[1]), C.byref(opts[1]), _ptr(ws), nbytes, _stream()),
+              "sinkhorn_pair")
+    return outs[0], outs[1]
+
+
 def sinkhorn_is_resident(B: int, K: int) -> bool:
     """True if a call of this shape runs as ONE resident kernel (else one streaming pass per iteration)."""
     return bool(_cabi.lib().timet_sinkhorn_resident(int(B), int(K)))

@@ -86,9 +86,14 @@ class StepRunner:
         if events is not None:
             events["scores1"] = ops._record()
         # Q_source is written straight into frame 0 of the channel-last label tensor (time_tuning.py:144-147 without a copy)
-        ops.sinkhorn_from_scores(scores[:bs * N], self.eps, self.iters, self.world_size, out=self.labels[:, 0], share_sm=share_sm)
-        self.ev_q_src.record()
-        ops.sinkhorn_from_scores(scores[bs * N:], self.eps, self.iters, self.world_size, out=self.q_tgt, share_sm=share_sm)
+        if share_sm:
+            ops.sinkhorn_from_scores(scores[:bs * N], self.eps, self.iters, self.world_size, out=self.labels[:, 0], share_sm=True)
+            self.ev_q_src.record()
+            ops.sinkhorn_from_scores(scores[bs * N:], self.eps, self.iters, self.world_size, out=self.q_tgt, share_sm=True)
+        else:       # both assignments in one resident launch: each hides the other's reduction latency
+            ops.sinkhorn_pair_from_scores(scores[:bs * N], scores[bs * N:], self.eps, self.iters, self.world_size,
+                                          out0=self.labels[:, 0], out1=self.q_tgt)
+            self.ev_q_src.record()
         if events is not None:
             events["sinkhorn1"] = ops._record()
 
@@ -172,9 +177,9 @@ class HostStepPipeline:
                 self.d_backbone[c * cb:(c + 1) * cb].copy_(backbone[c * cb:(c + 1) * cb], non_blocking=True)
                 self.ev_chunk[c].record(self.copy_stream)
         main.wait_event(self.ev_head)
-        scores = ops.cosine_scores(self.d_head.reshape(2 * bs * N, self.dh), prototypes)
-        ops.sinkhorn_from_scores(scores[:bs * N], epsilon, sinkhorn_iterations, world_size, out=self.labels[:, 0])
-        ops.sinkhorn_from_scores(scores[bs * N:], epsilon, sinkhorn_iterations, world_size, out=self.q_tgt)
+        scores = ops.cosine_scores_multi([self.d_head[0].reshape(bs * N, self.dh), self.d_head[1].reshape(bs * N, self.dh)], prototypes)
+        ops.sinkhorn_pair_from_scores(scores[:bs * N], scores[bs * N:], epsilon, sinkhorn_iterations, world_size,
+                                      out0=self.labels[:, 0], out1=self.q_tgt)
         plan = ops._plan(cb, self.fs, sr, sr, self.D, K, n_last_frames, size_mask_neighborhood, topk, device=self.device)
         for c in range(self.chunks):
             main.wait_event(self.ev_chunk[c])
