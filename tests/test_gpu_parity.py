@@ -387,11 +387,15 @@ def test_sinkhorn_rows_beyond_shared_memory():
 
 
 @pytest.mark.parametrize("B,K,iters", [(32 * 784, 200, 10), (8 * 784, 200, 3), (4 * 196, 64, 1), (2 * 3136, 300, 10), (1000, 516, 4)])
-def test_sinkhorn_pair_is_two_single_calls(B, K, iters):
-    """timet_sinkhorn_pair (two problems, one resident launch, reductions overlapped) returns the bits of two single
-    calls -- resident pair where it fits, sequential fallback otherwise (K = 516)."""
+def test_sinkhorn_pair_is_two_single_calls(timet_env, B, K, iters):
+    """timet_sinkhorn_pair (two problems, one resident launch, reductions overlapped; opt-in TIMET_SK_PAIR=1) returns the
+    bits of two single calls -- resident pair where it fits, sequential fallback otherwise (K = 516) and by default."""
     s0, s1 = cu(synth.cosine_scores(B, K, seed=5)), cu(synth.cosine_scores(B, K, seed=6))
+    d0, d1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)           # default: two sequential resident calls
+    timet_env(TIMET_SK_PAIR="1")
     q0, q1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
+    timet_env(TIMET_SK_PAIR=None)
+    assert torch.equal(d0, q0) and torch.equal(d1, q1)
     r0, r1 = tb.sinkhorn_from_scores(s0, 0.05, iters), tb.sinkhorn_from_scores(s1, 0.05, iters)
     assert torch.equal(q0, r0) and torch.equal(q1, r1), ((q0 - r0).abs().max().item(), (q1 - r1).abs().max().item())
     assert_close(q1.cpu().numpy(), O.sinkhorn_scaling(s1.cpu().numpy(), 0.05, iters, dtype=np.float64), what="pair vs fp64 oracle")

@@ -49,7 +49,7 @@ int num_sms();
 struct EnvCfg {
     int tc_pflags, tc_flags, tc_stages, tc_nbuf, tc_clip_group;   // 0 = default
     bool tc_pair, tc_persist, tc_dyn, tc_trace;
-    bool sk_streaming, sk_no_pair;
+    bool sk_streaming, sk_pair;
     int sk_ustride;                                                // 0 = default
     int sc_stages;                                                 // cosine-scores GEMM ring depth (2 = two CTAs per SM, default; 4)
     int gather_batch;                                              // gather: label rows in flight per batch (0 = by topk)

@@ -210,11 +210,11 @@ static int ff_gather_launch_gb(const timet_ff_params &p, const FFLayout &L, floa
     return TIMET_OK;
 }
 
-// Gathered rows in flight per batch: the usual survivor count (topk, no ties) should need ONE batch -- the kernel is
-// bound by dependent L2 round trips per query, not by bandwidth.  5 for the training default topk = 5, else 4.
+// Gathered rows in flight per batch.  Measured at BASELINE configs[1] (topk 5): 4 -> 0.180 ms, 5 -> 0.220 ms (one round
+// trip per query but the two extra float4 per lane spill), 7 -> 0.332 ms; 4 is the default (env TIMET_GATHER_BATCH).
 int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
                      cudaStream_t st) {
-    const int gb = env_cfg().gather_batch ? env_cfg().gather_batch : (p.topk == 5 ? 5 : 4);
+    const int gb = env_cfg().gather_batch ? env_cfg().gather_batch : 4;
     if (gb == 5) return ff_gather_launch_gb<5>(p, L, labels, hard, ws, st);
     if (gb >= 7) return ff_gather_launch_gb<7>(p, L, labels, hard, ws, st);
     return ff_gather_launch_gb<4>(p, L, labels, hard, ws, st);

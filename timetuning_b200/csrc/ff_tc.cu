@@ -605,8 +605,9 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float
         float *sw = reinterpret_cast<float *>(ws + L.off_sel_w);
         int32_t *sk = reinterpret_cast<int32_t *>(ws + L.off_sel_k), *sc = reinterpret_cast<int32_t *>(ws + L.off_sel_cnt);
         unsigned long long *stt = reinterpret_cast<unsigned long long *>(ws + L.off_stats);
-        // one batch covers the usual candidate count: k plus the odd near-tie (<= 4 for k <= 3, <= 6 for k <= 5, else 8)
-        const int fb = env_cfg().fin_batch ? env_cfg().fin_batch : (p.topk <= 3 ? 4 : (p.topk <= 5 ? 6 : 8));
+        // candidate rows in flight per batch (env TIMET_FIN_BATCH).  Measured at BASELINE configs[1] (5.2 candidates per
+        // query): 4 -> 0.254 ms, 6 -> 0.261 ms, 8 -> 0.319 ms (registers / occupancy): 4 is the default
+        const int fb = env_cfg().fin_batch ? env_cfg().fin_batch : 4;
         if (fb <= 4)
             ff_finalize_kernel<4, 4><<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(p, L.N, S, L.nT, L.kw, cand, meta, sw, sk, sc, stt, redo_list, redo_count, L.queries);
         else if (fb <= 6)

@@ -978,7 +978,7 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
     int prank = 0, pws = 1;
     unsigned long long *pepoch = nullptr;
     const bool p2p = world_size > 1 && comm != nullptr && comm_p2p_info(comm, &peers, &prank, &pws, &pepoch) && pws == world_size && K <= P2P_MAX_K;
-    bool ok = (world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && !E.sk_no_pair && epsilon > 0.f &&
+    bool ok = (world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && E.sk_pair && epsilon > 0.f &&
               (input_kind == TIMET_SK_EXP || input_kind == TIMET_SK_SCORES) && sk_pair_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160 &&
               (int64_t)(iters / 2 + 1) * rgrid < (1 << SKR_CNT_BITS);
     for (int c = 0; c < 2 && ok; ++c) {
