@@ -557,11 +557,13 @@ def main():
                            "have fewer contexts, so this over-states the CPU path)")
             cpu = {"value": n / t * scale, "unit": "clips/s", "cores": thr, "kind": kind, "sample": "best of 3 after 1 warm-up; " + sample}
         if world > 1:
-            sk_path = "p2p (in-kernel NVLink peer stores + flags, one resident launch per call)" if ops._comm.get("p2p") else \
-                      "nccl (one ncclAllReduce of K floats per Sinkhorn pass on the library's own communicator)"
-            if not is_eval and not runner.sinkhorn_resident:
-                sk_path = ("streaming passes + " + ("in-kernel NVLink peer exchange" if ops._comm.get("p2p") else "ncclAllReduce per pass")
-                           + " (rows do not fit shared memory)")
+            mode = runner.sinkhorn_mode if not is_eval else "none"
+            launch = {"resident": "one resident launch per call", "hybrid": "one hybrid launch per call (rows partly re-read from L2 / HBM)",
+                      "streaming": "one launch per pass"}.get(mode, mode)
+            if mode == "streaming" or not ops._comm.get("p2p"):
+                sk_path = f"nccl (one ncclAllReduce of K floats per Sinkhorn pass on the library's own communicator; {launch})"
+            else:
+                sk_path = f"p2p (in-kernel NVLink peer stores + flags; {launch})"
             par = f"clips sharded over {world} GPUs, no data-path collective for Feature-Forwarding; Sinkhorn K-vector marginals: {sk_path}"
         else:
             sk_path, par = "single", "single GPU"

@@ -92,8 +92,9 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
 int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, int input_kind, float epsilon, int iters,
                         int world_size, timet_comm_t comm, float *q0, const timet_sinkhorn_opts *opts0, float *q1,
                         const timet_sinkhorn_opts *opts1, void *workspace, size_t workspace_bytes, timet_stream_t stream);
-/* 1 if a call of this shape runs as ONE resident kernel (rows of exp(S/eps) fit the SMs' shared memory), 0 if it runs
- * as one streaming pass per iteration */
+/* How a call of this shape runs: 1 = ONE resident kernel (all rows of exp(S/eps) fit the SMs' shared memory);
+ * 2 = ONE hybrid kernel (as many rows resident as fit, the rest re-read and re-exponentiated every iteration -- e.g.
+ * BASELINE configs[2] at 2 / 4 GPUs); 0 = one streaming launch per pass (K % 4 != 0, K > 512, TIMET_SK_STREAMING=1). */
 int timet_sinkhorn_resident(int64_t B, int K);
 
 /* ------------------------------------------------------------------ cosine scores

@@ -35,6 +35,11 @@ def main():
     B = 4 * 784 * ws
     scores = synth.cosine_scores(B, 200, seed=123)
     cases.append(("cfg3-slice", scores, 0.05, 10, O.sinkhorn_scaling(scores, 0.05, 10, dtype=np.float64)))
+    # rows beyond shared memory on every rank (configs[2] at 4 GPUs: 64 clips per rank): the hybrid one-launch kernel
+    big = synth.cosine_scores(64 * 784 * ws, 200, seed=124)
+    cases.append(("hybrid-64-clips-per-rank", big, 0.05, 10, O.sinkhorn_scaling(big, 0.05, 10, dtype=np.float64)))
+    if rank == 0:
+        print("sinkhorn path:", "p2p" if tb.ops._comm.get("p2p") else "nccl")
     for name, sc, eps, iters, want in cases:
         rows = tdist.shard_range(sc.shape[0], rank, ws)
         local = torch.from_numpy(sc[rows.start:rows.stop]).cuda()

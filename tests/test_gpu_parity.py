@@ -488,3 +488,24 @@ def test_exact_engine_vs_oracle_config5_grid():
         got = labels[0, 1:].permute(0, 2, 1).reshape(fs - 1, C, sr, sr).cpu().numpy()
         check_soft(got, ref, taint, what=f"56x56x768 engine {engine}")
         check_hard(hard[0].cpu().numpy(), ref[-1], taint[-1], what="56x56x768 hard")
+
+
+def test_sinkhorn_hybrid_kernel(timet_env):
+    """Rows beyond shared memory (configs[2] at 4 GPUs: 64 clips = 50 176 rows per rank): ONE hybrid launch (resident part +
+    re-read part) against the one-launch-per-pass streaming path and the fp64 oracle; bit-reproducible."""
+    B, K = 64 * 784, 200
+    assert tb.ops.sinkhorn_mode(B, K) == "hybrid" and tb.ops.sinkhorn_mode(32 * 784, K) == "resident"
+    scores = synth.cosine_scores(B, K, seed=93)
+    q = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
+    assert torch.equal(q, tb.sinkhorn_from_scores(cu(scores), 0.05, 10))
+    timet_env(TIMET_SK_STREAMING="1")
+    q_str = tb.sinkhorn_from_scores(cu(scores), 0.05, 10)
+    timet_env(TIMET_SK_STREAMING=None)
+    assert_close(q.cpu().numpy(), q_str.cpu().numpy(), atol=1e-6, rtol=1e-5, what="hybrid vs streaming")
+    assert_close(q.double().cpu().numpy(), O.sinkhorn_scaling(scores, 0.05, 10, dtype=np.float64), what="hybrid vs fp64 oracle")
+    # strided output and K = 300 (three float4 per lane)
+    s2 = synth.cosine_scores(40 * 784, 300, seed=94)
+    out = torch.zeros((40, 2, 784, 300), device="cuda")
+    tb.sinkhorn_from_scores(cu(s2), 0.05, 10, out=out[:, 0])
+    assert_close(out[:, 0].reshape(-1, 300).double().cpu().numpy(), O.sinkhorn_scaling(s2, 0.05, 10, dtype=np.float64), what="hybrid K=300")
+    assert (out[:, 1] == 0).all()

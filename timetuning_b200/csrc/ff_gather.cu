@@ -124,12 +124,12 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
                 const int c = c0 + lane, c2 = c + 32;
                 const bool one = c < CV, two = c2 < CV;
                 V acc0 = ga_zero<V>(), acc1 = ga_zero<V>();
-                if (cnt >= 0) {
-                    ga_rows<V, GB>(acc0, acc1, w_l, k_l, cnt, clip_base, C, c, c2, one, two);
-                } else {
-                    // wide row (more than kw survivors: exact tie sets): -cnt entries in the pool at offset sel_k[0]
-                    ga_rows_wide<V>(acc0, acc1, wide_w, wide_k, __shfl_sync(0xffffffffu, k_l, 0), -cnt, clip_base, C, c, c2, one, two, lane);
-                }
+                // every lane holds the same cnt; taking it from a warp collective tells the compiler so (no per-shuffle
+                // reconvergence code around the loop below)
+                const int cnt_u = __reduce_max_sync(0xffffffffu, cnt);
+                ga_rows<V, GB>(acc0, acc1, w_l, k_l, cnt_u, clip_base, C, c, c2, one, two);
+                if (cnt_u < 0)   // wide row (more than kw survivors: exact tie sets): -cnt entries in the pool at offset sel_k[0]
+                    ga_rows_wide<V>(acc0, acc1, wide_w, wide_k, __shfl_sync(0xffffffffu, k_l, 0), -cnt_u, clip_base, C, c, c2, one, two, lane);
                 if (one) dst[c] = acc0;
                 if (two) dst[c2] = acc1;
             }

@@ -320,14 +320,33 @@ ff_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 // Per-candidate chains keep their i = lane, lane + 32, ... order (common.cuh), so the bits do not depend on BATCH.
 constexpr int FIN_WARPS = 8;
 constexpr int FIN_QPB = 64;                    // consecutive queries per CTA (neighbouring queries nominate neighbouring keys: L1 reuse)
+constexpr int FIN_BATCH = 4;                   // candidate rows in flight together (6 / 8 measured slower: registers, occupancy)
 
-template <int BATCH, int MINB>
-__global__ void __launch_bounds__(FIN_WARPS * 32, MINB)
-ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw,
+// Canonical xor-butterfly of FOUR accumulators at once ("transposed" reduction): after the xor-16 step a lane keeps two of
+// the four values, after the xor-8 step one; steps 4, 2, 1 finish it.  7 shuffles instead of 20, and every partial sum is
+// the same  v[l] + v[l ^ o]  in the same order as warp_sum (fp add is commutative), so the bits are those of common.cuh's
+// definition.  Returns the sum of acc[u] in the lanes with bit 4 == (u >> 1) and bit 3 == (u & 1).
+__device__ __forceinline__ float fin_reduce4(const float (&acc)[4], int lane) {
+    const bool hi4 = (lane & 16) != 0, hi3 = (lane & 8) != 0;
+    float k0 = hi4 ? acc[2] : acc[0], k1 = hi4 ? acc[3] : acc[1];
+    const float s0 = hi4 ? acc[0] : acc[2], s1 = hi4 ? acc[1] : acc[3];
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    float v = hi3 ? k1 : k0;
+    const float sv = hi3 ? k0 : k1;
+    v += __shfl_xor_sync(0xffffffffu, sv, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+__global__ void __launch_bounds__(FIN_WARPS * 32, 4)
+ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw, uint32_t w_magic,
                    const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_meta,
                    float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
                    unsigned long long *__restrict__ stats, int32_t *__restrict__ redo_list,
-                   unsigned int *__restrict__ redo_count, int64_t n_queries) {
+                   unsigned int *__restrict__ redo_count, uint32_t n_queries) {
     __shared__ unsigned long long s_stat[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
@@ -335,93 +354,100 @@ ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw,
     const int W = p.grid_w;
     const int n4 = S.n4;
     unsigned long long st_sel = 0, st_ties = 0, st_cand = 0;
-    const int64_t q_end = min(n_queries, ((int64_t)blockIdx.x + 1) * FIN_QPB);
-    int64_t qid = (int64_t)blockIdx.x * FIN_QPB + warp;
+    // index arithmetic without per-query divisions: (frame, patch) of the CTA's first query once, then increments
+    const uint32_t q_first = blockIdx.x * (uint32_t)FIN_QPB;
+    const uint32_t q_end = min(n_queries, q_first + (uint32_t)FIN_QPB);
+    const uint32_t ft0 = q_first / (uint32_t)N;              // clip * nT + tt
+    const uint32_t clip0 = ft0 / (uint32_t)nT;
+    int i = (int)(q_first - ft0 * (uint32_t)N) + warp;
+    int tt = (int)(ft0 - clip0 * (uint32_t)nT), clip = (int)clip0;
+    uint32_t qid = q_first + (uint32_t)warp;
     uint32_t m_next = 0u, c_next = 0u;
     if (qid < q_end) {
         m_next = __ldg(cand_meta + qid);
-        if (lane < FF_CAND_STORE) c_next = __ldg(cand + qid * FF_CAND_STORE + lane);
+        if (lane < FF_CAND_STORE) c_next = __ldg(cand + (size_t)qid * FF_CAND_STORE + lane);
     }
-    for (; qid < q_end; qid += FIN_WARPS) {
-        const uint32_t m0 = m_next, c_cur = c_next;
+    const int src_lane = ((lane & 2) << 3) | ((lane & 1) << 3);     // where fin_reduce4 leaves candidate (lane & 3)
+    for (; qid < q_end; qid += FIN_WARPS, i += FIN_WARPS) {
+        while (i >= N) { i -= N; if (++tt == nT) { tt = 0; ++clip; } }
+        // every lane loaded the same meta word; taking it from a warp collective tells the compiler that the candidate
+        // loops below are warp-uniform (no reconvergence code around their shuffles)
+        const uint32_t m0 = __reduce_max_sync(0xffffffffu, m_next), c_cur = c_next;
         if (qid + FIN_WARPS < q_end) {                 // next query's list: in flight during this query's evaluation
             m_next = __ldg(cand_meta + qid + FIN_WARPS);
-            if (lane < FF_CAND_STORE) c_next = __ldg(cand + (qid + FIN_WARPS) * FF_CAND_STORE + lane);
+            if (lane < FF_CAND_STORE) c_next = __ldg(cand + (size_t)(qid + FIN_WARPS) * FF_CAND_STORE + lane);
         }
         const int nc = (int)(m0 & 0xFFFFu);
         if ((m0 & 0x10000u) != 0u) {
             if (lane == 0) redo_list[atomicAdd(redo_count, 1u)] = (int32_t)qid;
             continue;
         }
-        const int clip = (int)(qid / ((int64_t)nT * N));
-        const int rem = (int)(qid - (int64_t)clip * nT * N);
-        const int tt = rem / N, i = rem - tt * N;
         const int t = p.t_begin + tt;
         const int64_t clip_row0 = (int64_t)clip * p.n_frames * N;
         const int64_t q_row = clip_row0 + (int64_t)t * N + i;
         const float4 *qrow = reinterpret_cast<const float4 *>(S.x + q_row * S.ld);
-        const int qr = i / W, qc = i - qr * W;
+        const int qr = (W == 1) ? i : (int)__umulhi((uint32_t)i, w_magic), qc = i - qr * W;   // i / W, i % W (exact for i < 65536)
         // lane j owns candidate j (nc <= FF_CAND_STORE)
         const bool has = lane < nc;
-        int32_t key = 0, krow = (int32_t)q_row;
+        int32_t key = 0x7fffffff, krow = (int32_t)q_row;
         if (has) {
             const uint32_t code = c_cur & 0x1FFFu;
             const int ci = (int)(code >> 10), wr = (int)((code >> 5) & 31u), wc = (int)(code & 31u);
             const int f = ctx_frame(t, p.n_last_frames, ci);
-            const int j = (qr - p.radius + wr) * W + (qc - p.radius + wc);
-            key = f * N + j;
+            key = f * N + (qr - p.radius + wr) * W + (qc - p.radius + wc);
             krow = (int32_t)(clip_row0 + key);
         }
         const float inv_q = __ldg(S.inv + q_row);
         const float inv_k = __ldg(S.inv + krow);
-        // warp-cooperative canonical dot, BATCH candidates at a time: the query row and all key rows of a batch are in
+        // warp-cooperative canonical dot, four candidates at a time: the query row and the key rows of a batch are in
         // flight together
         float my_dot = 0.f;
-        for (int c0 = 0; c0 < nc; c0 += BATCH) {
-            const float4 *kp[BATCH];
+        for (int c0 = 0; c0 < nc; c0 += FIN_BATCH) {
+            const float4 *kp[FIN_BATCH];
 #pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
+            for (int u = 0; u < FIN_BATCH; ++u) {
                 const int32_t row = __shfl_sync(0xffffffffu, krow, (c0 + u < nc) ? c0 + u : c0);
                 kp[u] = reinterpret_cast<const float4 *>(S.x + (int64_t)row * S.ld);
             }
-            float acc[BATCH];
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u) acc[u] = 0.f;
+            float acc[FIN_BATCH] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 3
             for (int e = lane; e < n4; e += 32) {
                 const float4 x = __ldg(qrow + e);
-                float4 y[BATCH];
+                float4 y[FIN_BATCH];
 #pragma unroll
-                for (int u = 0; u < BATCH; ++u) y[u] = __ldg(kp[u] + e);
+                for (int u = 0; u < FIN_BATCH; ++u) y[u] = __ldg(kp[u] + e);
 #pragma unroll
-                for (int u = 0; u < BATCH; ++u) acc[u] = fma4_chain(acc[u], x, y[u]);
+                for (int u = 0; u < FIN_BATCH; ++u) acc[u] = fma4_chain(acc[u], x, y[u]);
             }
-#pragma unroll
-            for (int u = 0; u < BATCH; ++u) {
-                const float sdot = warp_sum(acc[u]);
-                if (lane == c0 + u) my_dot = sdot;
-            }
+            const float red = fin_reduce4(acc, lane);
+            const float mine = __shfl_sync(0xffffffffu, red, src_lane);
+            if ((lane >> 2) == (c0 >> 2)) my_dot = mine;
         }
-        // canonical order (affinity desc, key asc) by counting: rank_j = #candidates that precede candidate j
+        // reference selection (mask_propagation.py:432-436) on the <= 16 exact affinities: canonical order (affinity desc,
+        // key asc) by counting, k-th value, everything >= it kept (ties), normalised; lane j scatters its entry to slot rank_j
         const float my_aff = has ? affinity_from_sim(sim_from_dot(my_dot, inv_q, inv_k), p.temperature) : -1.f;
-        const int32_t my_key = has ? key : 0x7fffffff;
         int rank = 0;
         for (int j = 0; j < nc; ++j) {
             const float a = __shfl_sync(0xffffffffu, my_aff, j);
-            const int32_t kk = __shfl_sync(0xffffffffu, my_key, j);
-            rank += (a > my_aff || (a == my_aff && kk < my_key)) ? 1 : 0;
+            const int32_t kk = __shfl_sync(0xffffffffu, key, j);
+            rank += (a > my_aff || (a == my_aff && kk < key)) ? 1 : 0;
         }
-        TopList L;
-        list_init(L);
-        for (int j = 0; j < nc; ++j) {                 // lane r picks the candidate of rank r
-            const float a = __shfl_sync(0xffffffffu, my_aff, j);
-            const int32_t kk = __shfl_sync(0xffffffffu, my_key, j);
-            const int r = __shfl_sync(0xffffffffu, rank, j);
-            if (r == lane) { L.v = a; L.key = kk; }
+        float kth = -1.f;                               // fewer than k candidates (tiny windows): all kept
+        if (nc >= p.topk) {
+            const unsigned who = __ballot_sync(0xffffffffu, has && rank == p.topk - 1);
+            kth = __shfl_sync(0xffffffffu, my_aff, __ffs(who) - 1);
         }
-        L.cnt = nc;
-        if (nc >= p.topk) L.kth = __shfl_sync(0xffffffffu, L.v, p.topk - 1);
-        const int m = list_finish(L, p.topk, kw, lane, sel_w + qid * kw, sel_k + qid * kw, sel_cnt + qid);   // m <= nc <= kw
+        const bool keep = has && my_aff >= kth;
+        const int m = __popc(__ballot_sync(0xffffffffu, keep));                 // m <= nc <= kw
+        const float sum = warp_sum(keep ? my_aff : 0.f);
+        float *w_out = sel_w + (size_t)qid * kw;
+        int32_t *k_out = sel_k + (size_t)qid * kw;
+        const int slot = has ? rank : lane;             // ranks are a permutation of 0..nc-1; lanes >= nc fill their own slot
+        if (slot < kw) {
+            w_out[slot] = keep ? __fdiv_rn(my_aff, sum) : 0.f;
+            k_out[slot] = keep ? key : -1;
+        }
+        if (lane == 0) sel_cnt[qid] = m;
         st_sel += (unsigned long long)m;
         st_ties += (m > p.topk);
         st_cand += (unsigned long long)nc;
@@ -601,20 +627,12 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float
     int32_t *redo_list = reinterpret_cast<int32_t *>(ws + L.off_redo + 256);
     const FFSrc S = ff_src(p, L, feats, ws);
     const int64_t blocks = (L.queries + FIN_QPB - 1) / FIN_QPB;
-    {
-        float *sw = reinterpret_cast<float *>(ws + L.off_sel_w);
-        int32_t *sk = reinterpret_cast<int32_t *>(ws + L.off_sel_k), *sc = reinterpret_cast<int32_t *>(ws + L.off_sel_cnt);
-        unsigned long long *stt = reinterpret_cast<unsigned long long *>(ws + L.off_stats);
-        // candidate rows in flight per batch (env TIMET_FIN_BATCH).  Measured at BASELINE configs[1] (5.2 candidates per
-        // query): 4 -> 0.254 ms, 6 -> 0.261 ms, 8 -> 0.319 ms (registers / occupancy): 4 is the default
-        const int fb = env_cfg().fin_batch ? env_cfg().fin_batch : 4;
-        if (fb <= 4)
-            ff_finalize_kernel<4, 4><<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(p, L.N, S, L.nT, L.kw, cand, meta, sw, sk, sc, stt, redo_list, redo_count, L.queries);
-        else if (fb <= 6)
-            ff_finalize_kernel<6, 3><<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(p, L.N, S, L.nT, L.kw, cand, meta, sw, sk, sc, stt, redo_list, redo_count, L.queries);
-        else
-            ff_finalize_kernel<8, 2><<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(p, L.N, S, L.nT, L.kw, cand, meta, sw, sk, sc, stt, redo_list, redo_count, L.queries);
-    }
+    TIMET_CHECK_ARG(L.queries < (1ll << 31), "ff_select: %lld queries exceed the 32-bit query index of the tensor-core engine", (long long)L.queries);
+    const uint32_t w_magic = (uint32_t)((0x100000000ull + (uint64_t)p.grid_w - 1) / (uint64_t)p.grid_w);   // ceil(2^32 / W)
+    ff_finalize_kernel<<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(
+        p, L.N, S, L.nT, L.kw, w_magic, cand, meta, reinterpret_cast<float *>(ws + L.off_sel_w),
+        reinterpret_cast<int32_t *>(ws + L.off_sel_k), reinterpret_cast<int32_t *>(ws + L.off_sel_cnt),
+        reinterpret_cast<unsigned long long *>(ws + L.off_stats), redo_list, redo_count, (uint32_t)L.queries);
     TIMET_LAUNCHED();
     // overflowed queries: exact scan (device-side count; a fixed small grid loops over the list)
     if ((rc = ff_select_exact_run(p, L, feats, ws, redo_list, redo_count, (int64_t)num_sms() * 8 * 8, st)) != TIMET_OK) return rc;

@@ -25,19 +25,56 @@ struct ScInputs {
     int64_t rows_each;
 };
 
+__device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+    return pk;
+}
+
+// One warp per row: x^ = x / max(||x||, 1e-12) (normalize = 1) or x itself -> [hi | lo] fp16, 2 * dhp wide.
+// dh % 4 == 0: 128-bit loads, the lane's slice kept in registers (dh <= 512), 64-bit stores of 4 halfs.
 __global__ void __launch_bounds__(256)
 scores_prep_kernel(ScInputs in, __half *__restrict__ out, int64_t rows, int dh, int dhp, int normalize) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    constexpr int KEEP = 4;
+    const bool vec = (dh & 3) == 0 && (dh >> 2) <= 32 * KEEP;
     for (int64_t row = warp; row < rows; row += nwarps) {
         const int64_t blk = row / in.rows_each;
         const float *src = in.x[blk] + (row - blk * in.rows_each) * dh;
+        __half *dst = out + row * 2 * dhp;
+        if (vec && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            float4 v[KEEP];
+            float ss = 0.f;
+#pragma unroll
+            for (int u = 0; u < KEEP; ++u) {
+                const int i = lane + 32 * u;
+                v[u] = (i < (dh >> 2)) ? __ldg(reinterpret_cast<const float4 *>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ss = fmaf(v[u].x, v[u].x, ss); ss = fmaf(v[u].y, v[u].y, ss); ss = fmaf(v[u].z, v[u].z, ss); ss = fmaf(v[u].w, v[u].w, ss);
+            }
+            ss = warp_sum(ss);
+            const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+#pragma unroll
+            for (int u = 0; u < KEEP; ++u) {
+                const int i = lane + 32 * u;
+                if (i < (dhp >> 2)) {
+                    const float a = __fdiv_rn(v[u].x, denom), b = __fdiv_rn(v[u].y, denom), c = __fdiv_rn(v[u].z, denom), d = __fdiv_rn(v[u].w, denom);
+                    const uint2 hi = pack_half4(a, b, c, d);
+                    const __half2 h01 = *reinterpret_cast<const __half2 *>(&hi.x), h23 = *reinterpret_cast<const __half2 *>(&hi.y);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    reinterpret_cast<uint2 *>(dst)[i] = hi;
+                    reinterpret_cast<uint2 *>(dst + dhp)[i] = pack_half4(a - f01.x, b - f01.y, c - f23.x, d - f23.y);
+                }
+            }
+            continue;
+        }
         float ss = 0.f;
         for (int i = lane; i < dh; i += 32) { const float v = src[i]; ss = fmaf(v, v, ss); }
         ss = warp_sum(ss);
         const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-        __half *dst = out + row * 2 * dhp;
         for (int i = lane; i < dhp; i += 32) {
             const float v = (i < dh) ? __fdiv_rn(src[i], denom) : 0.f;
             const __half hi = __float2half_rn(v);

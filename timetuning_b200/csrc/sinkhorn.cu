@@ -546,7 +546,7 @@ struct SkPairArgs {
     SkResArgs a[2];           // per-problem pointers / accumulators (shape fields equal); a[0] is the resident one
 };
 
-template <int NV4, int WARPS, bool RESIDENT>
+template <int NV4, int WARPS, bool RESIDENT, bool ZERO = true>
 __device__ __forceinline__ void skp_sweep(const SkResArgs &A, const float4 *E, int64_t row0, int nrows, const float *a_s,
                                           float4 (&acc)[NV4], bool last, int warp, int lane) {
     const int K = A.K, K4 = K >> 2;
@@ -555,7 +555,7 @@ __device__ __forceinline__ void skp_sweep(const SkResArgs &A, const float4 *E, i
     for (int v = 0; v < NV4; ++v) {
         const int i4 = lane + 32 * v;
         av[v] = (i4 < K4) ? reinterpret_cast<const float4 *>(a_s)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ZERO) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     constexpr int RPW = (NV4 <= 2) ? 2 : 1;
     for (int rl = warp; rl < nrows; rl += RPW * WARPS) {
@@ -769,6 +769,95 @@ static int sk_pair_launch(SkPairArgs &P, int grid, size_t smem, cudaStream_t st)
     return TIMET_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// HYBRID variant: ONE cooperative launch for a call whose rows do NOT fit shared memory (BASELINE configs[2] at 2 / 4
+// GPUs: 128 / 64 clips = 100 352 / 50 176 rows per rank).  Every CTA keeps as many of its rows of exp(S/eps) resident as
+// fit and re-reads the rest every iteration (from L2 while the score matrix fits there, else from HBM), recomputing exp --
+// bit-identical values.  Same reductions and the same in-kernel NVLink exchange as sk_resident; replaces the one-launch-
+// per-pass streaming path (+ one ncclAllReduce launch per pass at world_size > 1: 514 us per call at 8 ranks).
+template <int NV4>
+__global__ void __launch_bounds__(1024, 1) sk_hybrid(SkResArgs A, int res_rows) {
+    constexpr int THREADS = 1024, WARPS = THREADS / 32;
+    extern __shared__ float4 smem4[];
+    const int K = A.K, K4 = K >> 2;
+    float4 *E = smem4;                                                              // [res_rows, K4]
+    float *a_s = reinterpret_cast<float *>(smem4 + (size_t)res_rows * K4);          // [K]
+    float *u_s = a_s + K;                                                           // [K]
+    float *red = u_s + K;                                                           // [SKR_RED, K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_cta;
+    const int nrows = (int)max((int64_t)0, min((int64_t)A.rows_per_cta, A.B - row0));
+    const int nres = min(nrows, res_rows);
+
+    float4 acc[NV4];
+#pragma unroll
+    for (int v = 0; v < NV4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int rl = warp; rl < nrows; rl += WARPS) {
+        const float4 *src = reinterpret_cast<const float4 *>(A.in + (row0 + rl) * K);
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            if (i4 < K4) {
+                float4 e = __ldg(src + i4);
+                if (A.scores_mode) {
+                    e.x = expf(e.x * A.inv_eps); e.y = expf(e.y * A.inv_eps);
+                    e.z = expf(e.z * A.inv_eps); e.w = expf(e.w * A.inv_eps);
+                }
+                if (rl < nres) E[(size_t)rl * K4 + i4] = e;
+                acc[v].x += e.x; acc[v].y += e.y; acc[v].z += e.z; acc[v].w += e.w;
+            }
+        }
+    }
+    skr_fold_warps<NV4, WARPS>(red, acc, K, K4, warp, lane);
+    for (int i = threadIdx.x; i < K; i += THREADS) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
+        A.partials[(size_t)blockIdx.x * K + i] = t;
+    }
+    grid_barrier(A.bar, gridDim.x);
+    fold_partials<THREADS>(A.partials, gridDim.x, K, red, a_s, 0.f);
+    unsigned long long xch = A.epoch0;
+    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_s);
+    for (int i = threadIdx.x; i < K; i += THREADS) a_s[i] = __fdiv_rn(A.r, a_s[i]);
+    __syncthreads();
+
+    unsigned long long p0 = 0ull, p1 = 0ull;
+    for (int it = 0; it < A.iters; ++it) {
+        const bool last = (it == A.iters - 1);
+        skp_sweep<NV4, WARPS, true, true>(A, E, row0, nres, a_s, acc, last, warp, lane);
+        skp_sweep<NV4, WARPS, false, false>(A, nullptr, row0 + nres, nrows - nres, a_s, acc, last, warp, lane);
+        if (last) break;
+        skp_post<NV4, WARPS>(A, it, red, acc, warp, lane);
+        skp_wait<THREADS>(A, it, p0, p1, xch, a_s, u_s);
+    }
+}
+
+static bool sk_hybrid_plan(int64_t B, int K, int *grid, int *rows_per_cta, int *res_rows, size_t *smem) {
+    if (K % 4 != 0 || K > 128 * SK_MAX_V4) return false;
+    const int g = num_sms();
+    const int64_t rpc = (B + g - 1) / g;
+    const size_t fixed = (size_t)2 * K * 4 + (size_t)SKR_RED * K * 4;
+    const size_t room = (size_t)226 * 1024 - fixed;
+    int64_t rr = (int64_t)(room / ((size_t)K * 4));
+    if (rr > rpc) rr = rpc;
+    if (rr < 0) rr = 0;
+    *grid = (int)((B + rpc - 1) / rpc);
+    *rows_per_cta = (int)rpc;
+    *res_rows = (int)rr;
+    *smem = fixed + (size_t)rr * K * 4;
+    return rpc < (1ll << 30);
+}
+
+template <int NV4>
+static int sk_hybrid_launch(SkResArgs &A, int res_rows, int grid, size_t smem, cudaStream_t st) {
+    TIMET_CUDA(cudaFuncSetAttribute(sk_hybrid<NV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void *args[] = {&A, &res_rows};
+    TIMET_CUDA(cudaLaunchCooperativeKernel((const void *)sk_hybrid<NV4>, dim3(grid), dim3(1024), args, smem, st));
+    launch_counter()++;
+    return TIMET_OK;
+}
+
 static bool sk_resident_plan(int64_t B, int K, int *grid, int *rows_per_cta, size_t *smem) {
     if (K % 4 != 0 || K > 128 * SK_MAX_V4) return false;
     const int g = num_sms();
@@ -848,9 +937,12 @@ int timet_sinkhorn(const float *in, int64_t B, int K, int input_kind, float epsi
 }
 
 int timet_sinkhorn_resident(int64_t B, int K) {
-    int g, rpc;
+    int g, rpc, res;
     size_t smem;
-    return (B >= 1 && K >= 1 && sk_resident_plan(B, K, &g, &rpc, &smem) && g <= 160) ? 1 : 0;
+    if (B < 1 || K < 1 || env_cfg().sk_streaming) return 0;
+    if (sk_resident_plan(B, K, &g, &rpc, &smem) && g <= 160) return 1;
+    if (sk_hybrid_plan(B, K, &g, &rpc, &res, &smem) && g <= 160) return 2;
+    return 0;
 }
 
 int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
@@ -913,6 +1005,40 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
                 case 2: return sk_resident_launch<2>(R, rgrid, rsmem, st, share_sm);
                 case 3: return sk_resident_launch<3>(R, rgrid, rsmem, st, share_sm);
                 default: return sk_resident_launch<4>(R, rgrid, rsmem, st, share_sm);
+            }
+        }
+        // rows do not fit shared memory: hybrid kernel (resident part + re-read part), still one cooperative launch
+        int hgrid, hrpc, hres;
+        size_t hsmem;
+        if ((world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(q_out) & 15) == 0 && (ob_stride % 4) == 0 && !sk_resident_plan(B, K, &rgrid, &rpc, &rsmem) &&
+            sk_hybrid_plan(B, K, &hgrid, &hrpc, &hres, &hsmem) && hgrid <= 160 && (int64_t)(iters / 2 + 1) * hgrid < (1 << SKR_CNT_BITS)) {
+            float *partials = (float *)workspace;
+            const size_t bar_off = (size_t)322 * K * sizeof(float);
+            const size_t ufix_off = align_up(bar_off + 64, 256);
+            const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;
+            TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
+            SkResArgs R;
+            R.ustride = ustride;
+            int head = 1;
+            while ((1 << head) < iters / 2 + 2) ++head;
+            R.ufix_scale = ldexpf(1.0f, 47 - head);
+            R.ufix_inv = ldexpf(1.0f, head - 47);
+            R.ufix = (unsigned long long *)((char *)workspace + ufix_off);
+            R.out_block_rows = ob_rows; R.out_block_stride = ob_stride;
+            R.in = in; R.q_out = q_out; R.partials = partials; R.bar = (unsigned int *)((char *)workspace + bar_off);
+            R.B = B; R.K = K; R.iters = iters; R.rows_per_cta = hrpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
+            R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
+            R.r = 1.0f / (float)K; R.c = 1.0f / ((float)B * (float)world_size);
+            R.peers = p2p ? peers : nullptr; R.rank = prank; R.ws = p2p ? pws : 1;
+            R.epoch0 = p2p ? *pepoch : 0ull;
+            R.timeout_ns = (unsigned long long)(E.p2p_timeout_s * 1e9);
+            if (p2p) *pepoch += (unsigned long long)iters;
+            switch ((K / 4 + 31) / 32) {
+                case 1: return sk_hybrid_launch<1>(R, hres, hgrid, hsmem, st);
+                case 2: return sk_hybrid_launch<2>(R, hres, hgrid, hsmem, st);
+                case 3: return sk_hybrid_launch<3>(R, hres, hgrid, hsmem, st);
+                default: return sk_hybrid_launch<4>(R, hres, hgrid, hsmem, st);
             }
         }
     }

@@ -134,9 +134,14 @@ def sinkhorn_pair_from_scores(scores0, scores1, epsilon: float, nmb_iters: int, 
     return outs[0], outs[1]
 
 
+def sinkhorn_mode(B: int, K: int) -> str:
+    """How a Sinkhorn call of this shape runs: "resident" (one launch, all rows in shared memory), "hybrid" (one launch,
+    part of the rows re-read every iteration) or "streaming" (one launch per pass)."""
+    return ("streaming", "resident", "hybrid")[int(_cabi.lib().timet_sinkhorn_resident(int(B), int(K)))]
+
+
 def sinkhorn_is_resident(B: int, K: int) -> bool:
-    """True if a call of this shape runs as ONE resident kernel (else one streaming pass per iteration)."""
-    return bool(_cabi.lib().timet_sinkhorn_resident(int(B), int(K)))
+    return sinkhorn_mode(B, K) == "resident"
 
 
 def _sinkhorn_launch(x, kind, eps, iters, world_size, out=None, share_sm=False):

@@ -67,7 +67,8 @@ class StepRunner:
         self.labels = torch.empty((bs, fs, self.N, K), dtype=torch.float32, device=self.device)
         self.hard = torch.empty((bs, self.N), dtype=torch.int64, device=self.device)
         self.q_tgt = torch.empty((bs, self.N, K), dtype=torch.float32, device=self.device)
-        self.sinkhorn_resident = ops.sinkhorn_is_resident(bs * self.N, K)
+        self.sinkhorn_mode = ops.sinkhorn_mode(bs * self.N, K)
+        self.sinkhorn_resident = self.sinkhorn_mode == "resident"
         # the choreography above needs the one-launch resident Sinkhorn kernel and the tensor-core engine's event hook
         self.overlap = bool(overlap) and self.sinkhorn_resident and engine != ops.FF_EXACT and self.plan.tc_supported
         with torch.cuda.device(self.device):
