@@ -300,7 +300,9 @@ def dist_parity(rank, world, dev):
     if world == 2:      # produced by the reference itself under 2 gloo ranks (oracle/make_golden.py)
         g = dict(np.load(os.path.join(ROOT, "tests", "golden", "sinkhorn_ws2_b512_k200.npz")))
         cases.append(("reference-2-rank-fixture", g["scores"], float(g["epsilon"]), int(g["iters"]), g["q"]))
-    cases.append(("cfg3-slice", synth.cosine_scores(4 * 784 * world, 200, seed=123), 0.05, 10, None))
+    cases.append(("cfg3-slice (resident kernel)", synth.cosine_scores(4 * 784 * world, 200, seed=123), 0.05, 10, None))
+    # 64 clips per rank (BASELINE configs[2] at 4 GPUs): rows beyond shared memory -> the hybrid one-launch kernel
+    cases.append(("cfg3 64 clips per rank (hybrid kernel)", synth.cosine_scores(64 * 784 * world, 200, seed=124), 0.05, 10, None))
     for name, sc, eps, iters, want in cases:
         full_scores = torch.from_numpy(sc).to(dev)
         rows = tdist.shard_range(sc.shape[0], rank, world)

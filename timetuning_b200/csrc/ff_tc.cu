@@ -424,7 +424,7 @@ ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw, uint32_t w
             if ((lane >> 2) == (c0 >> 2)) my_dot = mine;
         }
         // reference selection (mask_propagation.py:432-436) on the <= 16 exact affinities: canonical order (affinity desc,
-        // key asc) by counting, k-th value, everything >= it kept (ties), normalised; lane j scatters its entry to slot rank_j
+        // key asc) by counting, k-th value, everything >= it kept (ties), normalised
         const float my_aff = has ? affinity_from_sim(sim_from_dot(my_dot, inv_q, inv_k), p.temperature) : -1.f;
         int rank = 0;
         for (int j = 0; j < nc; ++j) {
@@ -432,20 +432,22 @@ ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw, uint32_t w
             const int32_t kk = __shfl_sync(0xffffffffu, key, j);
             rank += (a > my_aff || (a == my_aff && kk < key)) ? 1 : 0;
         }
+        // lane r takes the candidate of rank r: the sorted layout of the exact engine's list (slot = lane), so that the
+        // normalising sum below adds the same values in the same butterfly positions -> identical bits
+        int src = 0;
+        for (int j = 0; j < nc; ++j)
+            if (__shfl_sync(0xffffffffu, rank, j) == lane) src = j;
+        const float s_aff = __shfl_sync(0xffffffffu, my_aff, src);
+        const int32_t s_key = __shfl_sync(0xffffffffu, key, src);
+        const bool in_list = lane < nc;
         float kth = -1.f;                               // fewer than k candidates (tiny windows): all kept
-        if (nc >= p.topk) {
-            const unsigned who = __ballot_sync(0xffffffffu, has && rank == p.topk - 1);
-            kth = __shfl_sync(0xffffffffu, my_aff, __ffs(who) - 1);
-        }
-        const bool keep = has && my_aff >= kth;
+        if (nc >= p.topk) kth = __shfl_sync(0xffffffffu, s_aff, p.topk - 1);
+        const bool keep = in_list && s_aff >= kth;
         const int m = __popc(__ballot_sync(0xffffffffu, keep));                 // m <= nc <= kw
-        const float sum = warp_sum(keep ? my_aff : 0.f);
-        float *w_out = sel_w + (size_t)qid * kw;
-        int32_t *k_out = sel_k + (size_t)qid * kw;
-        const int slot = has ? rank : lane;             // ranks are a permutation of 0..nc-1; lanes >= nc fill their own slot
-        if (slot < kw) {
-            w_out[slot] = keep ? __fdiv_rn(my_aff, sum) : 0.f;
-            k_out[slot] = keep ? key : -1;
+        const float sum = warp_sum(keep ? s_aff : 0.f);
+        if (lane < kw) {
+            sel_w[(size_t)qid * kw + lane] = keep ? __fdiv_rn(s_aff, sum) : 0.f;
+            sel_k[(size_t)qid * kw + lane] = keep ? s_key : -1;
         }
         if (lane == 0) sel_cnt[qid] = m;
         st_sel += (unsigned long long)m;

@@ -238,7 +238,9 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             if (DYN) {
                 if (lane == 0) ptx::mbar_wait(&ctl->item_bar[k & 3u], (k >> 2) & 1u);
                 __syncwarp();
-                id = ctl->item_id[k & 3u];
+                // every lane reads the same word; passing it through a warp collective tells ptxas so (the item geometry and all
+                // loop bounds derived from it stay in uniform registers, no reconvergence code around the warp collectives)
+                id = (int64_t)__reduce_max_sync(0xffffffffu, (unsigned)(ctl->item_id[k & 3u] + 1)) - 1;
             } else {
                 id = item_at(k, total);
             }
