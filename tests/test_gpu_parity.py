@@ -388,17 +388,25 @@ def test_sinkhorn_rows_beyond_shared_memory():
 
 @pytest.mark.parametrize("B,K,iters", [(32 * 784, 200, 10), (8 * 784, 200, 3), (4 * 196, 64, 1), (2 * 3136, 300, 10), (1000, 516, 4)])
 def test_sinkhorn_pair_is_two_single_calls(timet_env, B, K, iters):
-    """timet_sinkhorn_pair (two problems, one resident launch, reductions overlapped; opt-in TIMET_SK_PAIR=1) returns the
-    bits of two single calls -- resident pair where it fits, sequential fallback otherwise (K = 516) and by default."""
+    """timet_sinkhorn_pair: the source and target assignment of a step in ONE launch.  Default = DUAL (the two problems
+    side by side on half of the SMs each: same maths, another row partition -> equal to two single calls within fp32
+    summation order, bit-reproducible); TIMET_SK_DUAL=0 = one after the other and TIMET_SK_PAIR=1 = interleaved on the whole
+    grid, both bit-identical to two single calls; K = 516 exercises the sequential fall-back."""
     s0, s1 = cu(synth.cosine_scores(B, K, seed=5)), cu(synth.cosine_scores(B, K, seed=6))
-    d0, d1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)           # default: two sequential resident calls
-    timet_env(TIMET_SK_PAIR="1")
-    q0, q1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
-    timet_env(TIMET_SK_PAIR=None)
-    assert torch.equal(d0, q0) and torch.equal(d1, q1)
     r0, r1 = tb.sinkhorn_from_scores(s0, 0.05, iters), tb.sinkhorn_from_scores(s1, 0.05, iters)
+    d0, d1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)           # default: dual
+    e0, e1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
+    assert torch.equal(d0, e0) and torch.equal(d1, e1), "dual mode must be bit-reproducible"
+    assert_close(d0.cpu().numpy(), r0.cpu().numpy(), atol=1e-7, rtol=2e-5, what="dual vs single (0)")
+    assert_close(d1.cpu().numpy(), r1.cpu().numpy(), atol=1e-7, rtol=2e-5, what="dual vs single (1)")
+    assert_close(d1.cpu().numpy(), O.sinkhorn_scaling(s1.cpu().numpy(), 0.05, iters, dtype=np.float64), what="dual vs fp64 oracle")
+    timet_env(TIMET_SK_DUAL="0")
+    q0, q1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
+    assert torch.equal(q0, r0) and torch.equal(q1, r1)
+    timet_env(TIMET_SK_DUAL="0", TIMET_SK_PAIR="1")
+    q0, q1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
+    timet_env(TIMET_SK_DUAL=None, TIMET_SK_PAIR=None)
     assert torch.equal(q0, r0) and torch.equal(q1, r1), ((q0 - r0).abs().max().item(), (q1 - r1).abs().max().item())
-    assert_close(q1.cpu().numpy(), O.sinkhorn_scaling(s1.cpu().numpy(), 0.05, iters, dtype=np.float64), what="pair vs fp64 oracle")
 
 
 def test_sinkhorn_strided_output_into_label_frames():
@@ -409,12 +417,13 @@ def test_sinkhorn_strided_output_into_label_frames():
     labels = torch.full((bs, fs, N, K), -1.0, device="cuda")
     flat = torch.empty((bs, N, K), device="cuda")
     tb.sinkhorn_pair_from_scores(s0, s1, 0.05, 10, out0=labels[:, 0], out1=flat)
-    assert torch.equal(labels[:, 0].reshape(bs * N, K), tb.sinkhorn_from_scores(s0, 0.05, 10))
-    assert torch.equal(flat.reshape(bs * N, K), tb.sinkhorn_from_scores(s1, 0.05, 10))
+    d0, d1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, 10)
+    assert torch.equal(labels[:, 0].reshape(bs * N, K), d0) and torch.equal(flat.reshape(bs * N, K), d1)
+    assert_close(d0.cpu().numpy(), tb.sinkhorn_from_scores(s0, 0.05, 10).cpu().numpy(), atol=1e-7, rtol=2e-5, what="pair vs single")
     assert (labels[:, 1:] == -1).all(), "other frames untouched"
     lab2 = torch.full((bs, fs, N, K), -1.0, device="cuda")
     tb.sinkhorn_from_scores(s0, 0.05, 10, out=lab2[:, 0])
-    assert torch.equal(lab2, labels)
+    assert torch.equal(lab2[:, 0].reshape(bs * N, K), tb.sinkhorn_from_scores(s0, 0.05, 10)) and (lab2[:, 1:] == -1).all()
     with pytest.raises(ValueError):
         tb.sinkhorn_from_scores(s0, 0.05, 10, out=labels[:, 0, :, :100])
 

@@ -57,7 +57,7 @@ struct Comm {
     void *p2p_local = nullptr;                 // this rank's P2PBuf (cudaMalloc'ed here, written by the peers)
     void *p2p_peers_host[P2P_MAX_RANKS] = {};   // device pointers of every rank's P2PBuf (own at [rank])
     void **p2p_peers_dev = nullptr;            // the same table in device memory
-    unsigned long long p2p_epoch = 0;          // exchanges performed so far (identical on every rank)
+    unsigned long long p2p_epoch[2] = {0, 0};  // exchanges performed so far per channel (identical on every rank)
     bool p2p_ready = false;
 };
 
@@ -82,7 +82,7 @@ int comm_allreduce_f32(timet_comm_t comm, float *buf, int64_t n, cudaStream_t st
 bool comm_p2p_info(timet_comm_t comm, void ***peers_dev, int *rank, int *ws, unsigned long long **epoch) {
     Comm *c = (Comm *)comm;
     if (!c || !c->p2p_ready) return false;
-    *peers_dev = c->p2p_peers_dev; *rank = c->rank; *ws = c->world_size; *epoch = &c->p2p_epoch;
+    *peers_dev = c->p2p_peers_dev; *rank = c->rank; *ws = c->world_size; *epoch = c->p2p_epoch;
     return true;
 }
 
@@ -125,8 +125,8 @@ int timet_comm_p2p_handle(timet_comm_t comm, void *handle_out) {
     Comm *c = (Comm *)comm;
     TIMET_CHECK_ARG(c->world_size <= P2P_MAX_RANKS, "comm_p2p: world size %d > %d", c->world_size, P2P_MAX_RANKS);
     if (!c->p2p_local) {
-        TIMET_CUDA(cudaMalloc(&c->p2p_local, sizeof(P2PBuf)));
-        TIMET_CUDA(cudaMemset(c->p2p_local, 0, sizeof(P2PBuf)));
+        TIMET_CUDA(cudaMalloc(&c->p2p_local, 2 * sizeof(P2PBuf)));          // two exchange channels
+        TIMET_CUDA(cudaMemset(c->p2p_local, 0, 2 * sizeof(P2PBuf)));
         TIMET_CUDA(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
@@ -148,7 +148,7 @@ int timet_comm_p2p_connect(timet_comm_t comm, const void *all_handles) {
     }
     TIMET_CUDA(cudaMalloc((void **)&c->p2p_peers_dev, sizeof(void *) * P2P_MAX_RANKS));
     TIMET_CUDA(cudaMemcpy(c->p2p_peers_dev, c->p2p_peers_host, sizeof(void *) * P2P_MAX_RANKS, cudaMemcpyHostToDevice));
-    c->p2p_epoch = 0;
+    c->p2p_epoch[0] = c->p2p_epoch[1] = 0;
     c->p2p_ready = true;
     return TIMET_OK;
 }

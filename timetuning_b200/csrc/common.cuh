@@ -49,7 +49,7 @@ int num_sms();
 struct EnvCfg {
     int tc_pflags, tc_flags, tc_stages, tc_nbuf, tc_clip_group;   // 0 = default
     bool tc_pair, tc_persist, tc_dyn, tc_trace;
-    bool sk_streaming, sk_pair;
+    bool sk_streaming, sk_pair, sk_no_dual;
     int sk_ustride;                                                // 0 = default
     int sc_stages;                                                 // cosine-scores GEMM ring depth (2 = two CTAs per SM, default; 4)
     int gather_batch;                                              // gather: label rows in flight per batch (0 = by topk)
@@ -67,6 +67,7 @@ struct P2PBuf {
     unsigned long long pad[16];
     float slot[3][P2P_MAX_RANKS][P2P_MAX_K];         // slot[e % 3][src] = src's K-vector of exchange e
 };
+// *epoch points at the two per-channel exchange counters (every rank's buffer is P2PBuf[2])
 bool comm_p2p_info(timet_comm_t comm, void ***peers_dev, int *rank, int *ws, unsigned long long **epoch);
 
 // ------------------------------------------------------------------ FF workspace layout

@@ -275,8 +275,10 @@ struct SkResArgs {
     unsigned long long *ufix; // [2, K * ustride] fixed-point marginal accumulators with arrival counts (zeroed before launch)
     float ufix_scale, ufix_inv; // 2^sbits and 2^-sbits of the fixed-point part
     int ustride;              // u64 elements between two accumulators (SKR_USTRIDE: every accumulator in its own 256 B L2 block)
-    void *const *peers;       // world_size > 1: every rank's P2PBuf (NVLink peer memory), else nullptr
+    void *const *peers;       // world_size > 1: every rank's P2PBuf[2] (NVLink peer memory), else nullptr
     int rank, ws;
+    int chan;                 // exchange channel (P2PBuf index): two problems running side by side use one each
+    int g_first, g_size;      // CTAs [g_first, g_first + g_size) of the launch work on this problem (0 / 0 = the whole grid)
     unsigned long long epoch0; // exchanges completed before this call (same on every rank)
     unsigned long long timeout_ns; // patience of the in-kernel waits (env TIMET_P2P_TIMEOUT_S, default 10 min)
     int64_t B;
@@ -333,16 +335,16 @@ __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[N
 template <int SKR_THREADS>
 __device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long long e, float *vec) {
     const int K = A.K;
-    P2PBuf *own = reinterpret_cast<P2PBuf *>(A.peers[A.rank]);
+    P2PBuf *own = reinterpret_cast<P2PBuf *>(A.peers[A.rank]) + A.chan;
     const int slot = (int)(e % 3ull);
-    if (blockIdx.x == 0) {
+    if ((int)blockIdx.x == A.g_first) {
         for (int p = 0; p < A.ws; ++p) {
-            float *dst = reinterpret_cast<P2PBuf *>(A.peers[p])->slot[slot][A.rank];
+            float *dst = (reinterpret_cast<P2PBuf *>(A.peers[p]) + A.chan)->slot[slot][A.rank];
             for (int i = threadIdx.x; i < K; i += SKR_THREADS) dst[i] = vec[i];
         }
         __syncthreads();                       // bar.sync + the release below (system scope) cover every thread's stores
         if ((int)threadIdx.x < A.ws) {
-            unsigned long long *f = &reinterpret_cast<P2PBuf *>(A.peers[threadIdx.x])->flag[A.rank];
+            unsigned long long *f = &(reinterpret_cast<P2PBuf *>(A.peers[threadIdx.x]) + A.chan)->flag[A.rank];
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e + 1ull) : "memory");
         }
     }
@@ -647,7 +649,7 @@ __device__ __forceinline__ void skp_wait(const SkResArgs &A, int it, unsigned lo
     const int i = threadIdx.x;
     if (i < K) {
         unsigned long long *acc_i = A.ufix + (size_t)(it & 1) * K * A.ustride + (size_t)i * A.ustride;
-        const unsigned long long want = (unsigned long long)((it >> 1) + 1) * gridDim.x;
+        const unsigned long long want = (unsigned long long)((it >> 1) + 1) * (unsigned)(A.g_size ? A.g_size : (int)gridDim.x);
         unsigned long long v, t0 = 0ull;
         unsigned int spins = 0;
         do {
@@ -776,16 +778,23 @@ static int sk_pair_launch(SkPairArgs &P, int grid, size_t smem, cudaStream_t st)
 // bit-identical values.  Same reductions and the same in-kernel NVLink exchange as sk_resident; replaces the one-launch-
 // per-pass streaming path (+ one ncclAllReduce launch per pass at world_size > 1: 514 us per call at 8 ranks).
 template <int NV4>
-__global__ void __launch_bounds__(1024, 1) sk_hybrid(SkResArgs A, int res_rows) {
+__global__ void __launch_bounds__(1024, 1) sk_hybrid(SkPairArgs P, int nprob, int res_rows) {
     constexpr int THREADS = 1024, WARPS = THREADS / 32;
     extern __shared__ float4 smem4[];
+    // nprob = 2: the two problems run SIDE BY SIDE, each on half of the grid (DUAL mode).  A Sinkhorn call is bound by the
+    // latency of its ~10 dependent grid-wide reductions, not by the sweep, so a problem loses little on half of the SMs
+    // -- and the two calls of a training step (time_tuning.py:268,275) then overlap completely instead of queueing.
+    const int G = (int)gridDim.x / nprob;
+    const int which = (int)blockIdx.x / G;
+    const SkResArgs &A = P.a[which];
+    const int lb = (int)blockIdx.x - which * G;
     const int K = A.K, K4 = K >> 2;
     float4 *E = smem4;                                                              // [res_rows, K4]
     float *a_s = reinterpret_cast<float *>(smem4 + (size_t)res_rows * K4);          // [K]
     float *u_s = a_s + K;                                                           // [K]
     float *red = u_s + K;                                                           // [SKR_RED, K]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_cta;
+    const int64_t row0 = (int64_t)lb * A.rows_per_cta;
     const int nrows = (int)max((int64_t)0, min((int64_t)A.rows_per_cta, A.B - row0));
     const int nres = min(nrows, res_rows);
 
@@ -813,10 +822,10 @@ __global__ void __launch_bounds__(1024, 1) sk_hybrid(SkResArgs A, int res_rows) 
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
-        A.partials[(size_t)blockIdx.x * K + i] = t;
+        A.partials[(size_t)lb * K + i] = t;
     }
-    grid_barrier(A.bar, gridDim.x);
-    fold_partials<THREADS>(A.partials, gridDim.x, K, red, a_s, 0.f);
+    grid_barrier(A.bar, (unsigned)G);                   // the CTAs of this problem only (own counter)
+    fold_partials<THREADS>(A.partials, (unsigned)G, K, red, a_s, 0.f);
     unsigned long long xch = A.epoch0;
     if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_s);
     for (int i = threadIdx.x; i < K; i += THREADS) a_s[i] = __fdiv_rn(A.r, a_s[i]);
@@ -833,9 +842,9 @@ __global__ void __launch_bounds__(1024, 1) sk_hybrid(SkResArgs A, int res_rows) 
     }
 }
 
-static bool sk_hybrid_plan(int64_t B, int K, int *grid, int *rows_per_cta, int *res_rows, size_t *smem) {
+static bool sk_hybrid_plan(int64_t B, int K, int *grid, int *rows_per_cta, int *res_rows, size_t *smem, int g = 0) {
     if (K % 4 != 0 || K > 128 * SK_MAX_V4) return false;
-    const int g = num_sms();
+    if (g <= 0) g = num_sms();
     const int64_t rpc = (B + g - 1) / g;
     const size_t fixed = (size_t)2 * K * 4 + (size_t)SKR_RED * K * 4;
     const size_t room = (size_t)226 * 1024 - fixed;
@@ -850,9 +859,9 @@ static bool sk_hybrid_plan(int64_t B, int K, int *grid, int *rows_per_cta, int *
 }
 
 template <int NV4>
-static int sk_hybrid_launch(SkResArgs &A, int res_rows, int grid, size_t smem, cudaStream_t st) {
+static int sk_hybrid_launch(SkPairArgs &P, int nprob, int res_rows, int grid, size_t smem, cudaStream_t st) {
     TIMET_CUDA(cudaFuncSetAttribute(sk_hybrid<NV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void *args[] = {&A, &res_rows};
+    void *args[] = {&P, &nprob, &res_rows};
     TIMET_CUDA(cudaLaunchCooperativeKernel((const void *)sk_hybrid<NV4>, dim3(grid), dim3(1024), args, smem, st));
     launch_counter()++;
     return TIMET_OK;
@@ -984,6 +993,7 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
             const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;   // 1 = packed accumulators (for comparison)
             TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
             SkResArgs R;
+            R.chan = 0; R.g_first = 0; R.g_size = 0;
             R.ustride = ustride;
             // 48 data bits: the marginals of one iteration sum to <= 1 and a buffer accumulates ceil(iters / 2) of them
             int head = 1;
@@ -1018,7 +1028,9 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
             const size_t ufix_off = align_up(bar_off + 64, 256);
             const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;
             TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
-            SkResArgs R;
+            SkPairArgs HP;
+            SkResArgs &R = HP.a[0];
+            R.chan = 0; R.g_first = 0; R.g_size = hgrid;
             R.ustride = ustride;
             int head = 1;
             while ((1 << head) < iters / 2 + 2) ++head;
@@ -1035,10 +1047,10 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
             R.timeout_ns = (unsigned long long)(E.p2p_timeout_s * 1e9);
             if (p2p) *pepoch += (unsigned long long)iters;
             switch ((K / 4 + 31) / 32) {
-                case 1: return sk_hybrid_launch<1>(R, hres, hgrid, hsmem, st);
-                case 2: return sk_hybrid_launch<2>(R, hres, hgrid, hsmem, st);
-                case 3: return sk_hybrid_launch<3>(R, hres, hgrid, hsmem, st);
-                default: return sk_hybrid_launch<4>(R, hres, hgrid, hsmem, st);
+                case 1: return sk_hybrid_launch<1>(HP, 1, hres, hgrid, hsmem, st);
+                case 2: return sk_hybrid_launch<2>(HP, 1, hres, hgrid, hsmem, st);
+                case 3: return sk_hybrid_launch<3>(HP, 1, hres, hgrid, hsmem, st);
+                default: return sk_hybrid_launch<4>(HP, 1, hres, hgrid, hsmem, st);
             }
         }
     }
@@ -1112,6 +1124,54 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
         ok = (reinterpret_cast<uintptr_t>(in[c]) & 15) == 0 && (reinterpret_cast<uintptr_t>(qo[c]) & 15) == 0 && (obs % 4) == 0 &&
              (obr <= 0 || (obs >= obr * K && B % obr == 0));
     }
+    // ---- DUAL: the two problems side by side on half of the SMs each (sk_hybrid with nprob = 2), default
+    {
+        int dgrid, drpc, dres;
+        size_t dsmem;
+        const int half = num_sms() / 2;
+        bool dual = (world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && !E.sk_pair && !E.sk_no_dual && epsilon > 0.f &&
+                    (input_kind == TIMET_SK_EXP || input_kind == TIMET_SK_SCORES) && half >= 1 &&
+                    sk_hybrid_plan(B, K, &dgrid, &drpc, &dres, &dsmem, half) && dgrid <= 160 &&
+                    (int64_t)(iters / 2 + 1) * dgrid < (1 << SKR_CNT_BITS);
+        for (int c = 0; c < 2 && dual; ++c) {
+            const int64_t obr = op[c] ? op[c]->out_block_rows : 0, obs = op[c] ? op[c]->out_block_stride : 0;
+            dual = (reinterpret_cast<uintptr_t>(in[c]) & 15) == 0 && (reinterpret_cast<uintptr_t>(qo[c]) & 15) == 0 && (obs % 4) == 0 &&
+                   (obr <= 0 || (obs >= obr * K && B % obr == 0));
+        }
+        if (dual) {
+            SkPairArgs P;
+            const size_t bar_off = (size_t)322 * K * sizeof(float);
+            const size_t ufix_off = align_up(bar_off + 64, 256);
+            const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;
+            int head = 1;
+            while ((1 << head) < iters / 2 + 2) ++head;
+            for (int c = 0; c < 2; ++c) {
+                TIMET_CUDA(cudaMemsetAsync(wsp[c] + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
+                SkResArgs &R = P.a[c];
+                R.chan = c; R.g_first = c * dgrid; R.g_size = dgrid;
+                R.ustride = ustride;
+                R.ufix_scale = ldexpf(1.0f, 47 - head);
+                R.ufix_inv = ldexpf(1.0f, head - 47);
+                R.ufix = (unsigned long long *)(wsp[c] + ufix_off);
+                R.out_block_rows = op[c] ? op[c]->out_block_rows : 0;
+                R.out_block_stride = op[c] ? op[c]->out_block_stride : 0;
+                R.in = in[c]; R.q_out = qo[c]; R.partials = (float *)wsp[c]; R.bar = (unsigned int *)(wsp[c] + bar_off);
+                R.B = B; R.K = K; R.iters = iters; R.rows_per_cta = drpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
+                R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
+                R.r = 1.0f / (float)K; R.c = 1.0f / ((float)B * (float)world_size);
+                R.peers = p2p ? peers : nullptr; R.rank = prank; R.ws = p2p ? pws : 1;
+                R.epoch0 = p2p ? pepoch[c] : 0ull;
+                R.timeout_ns = (unsigned long long)(E.p2p_timeout_s * 1e9);
+                if (p2p) pepoch[c] += (unsigned long long)iters;       // pass 0 + (iters - 1) iterations exchange a vector
+            }
+            switch ((K / 4 + 31) / 32) {
+                case 1: return sk_hybrid_launch<1>(P, 2, dres, 2 * dgrid, dsmem, st);
+                case 2: return sk_hybrid_launch<2>(P, 2, dres, 2 * dgrid, dsmem, st);
+                case 3: return sk_hybrid_launch<3>(P, 2, dres, 2 * dgrid, dsmem, st);
+                default: return sk_hybrid_launch<4>(P, 2, dres, 2 * dgrid, dsmem, st);
+            }
+        }
+    }
     if (!ok) {      // not a resident pair: two independent calls (each validates its own arguments)
         int rc = timet_sinkhorn_ex(in0, B, K, input_kind, epsilon, iters, world_size, comm, q0, opts0, wsp[0], one, stream);
         if (rc != TIMET_OK) return rc;
@@ -1126,6 +1186,7 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
     for (int c = 0; c < 2; ++c) {
         TIMET_CUDA(cudaMemsetAsync(wsp[c] + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
         SkResArgs &R = P.a[c];
+        R.chan = 0; R.g_first = 0; R.g_size = 0;
         R.ustride = ustride;
         R.ufix_scale = ldexpf(1.0f, 47 - head);
         R.ufix_inv = ldexpf(1.0f, head - 47);
