@@ -562,6 +562,8 @@ def main():
             mode = runner.sinkhorn_mode if not is_eval else "none"
             launch = {"resident": "one resident launch per call", "hybrid": "one hybrid launch per call (rows partly re-read from L2 / HBM)",
                       "streaming": "one launch per pass"}.get(mode, mode)
+            if not is_eval and runner.sinkhorn_pair_mode == "dual" and not args.overlap:
+                launch = "ONE launch for both calls of the step, side by side on half of the SMs each, one exchange channel each"
             if mode == "streaming" or not ops._comm.get("p2p"):
                 sk_path = f"nccl (one ncclAllReduce of K floats per Sinkhorn pass on the library's own communicator; {launch})"
             else:

@@ -85,13 +85,18 @@ typedef struct timet_sinkhorn_opts {
 int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
                       timet_comm_t comm, float *q_out, const timet_sinkhorn_opts *opts, void *workspace,
                       size_t workspace_bytes, timet_stream_t stream);
-/* Two problems of the same shape (B, K, kind, eps, iters) in ONE resident launch: the source and the target assignment
- * of a training step (time_tuning.py:268,275).  While one problem waits for its grid-wide marginal reduction the CTAs
- * sweep the other; results are bit-identical to two timet_sinkhorn_ex calls.  workspace: 2 x
- * timet_sinkhorn_workspace_bytes(B, K).  Falls back to two sequential calls when the pair does not fit the SMs. */
+/* Two problems of the same shape (B, K, kind, eps, iters) in ONE launch: the source and the target assignment of a
+ * training step (time_tuning.py:268,275).  A call is bound by the latency of its dependent grid-wide reductions, so the
+ * two problems run SIDE BY SIDE on half of the SMs each (own reduction counters, own NVLink exchange channel) and overlap
+ * completely; rows that do not fit half of the shared memory are re-read from L2.  Same maths as timet_sinkhorn_ex on
+ * another row partition (equal within fp32 summation order, bit-reproducible).  workspace: 2 x
+ * timet_sinkhorn_workspace_bytes(B, K).  Falls back to two sequential calls where it does not apply. */
 int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, int input_kind, float epsilon, int iters,
                         int world_size, timet_comm_t comm, float *q0, const timet_sinkhorn_opts *opts0, float *q1,
                         const timet_sinkhorn_opts *opts1, void *workspace, size_t workspace_bytes, timet_stream_t stream);
+/* How timet_sinkhorn_pair runs this shape: 1 = DUAL (one launch, the two problems side by side on half of the SMs each:
+ * the default), 2 = interleaved on the whole grid (TIMET_SK_PAIR=1), 0 = two timet_sinkhorn_ex calls one after the other */
+int timet_sinkhorn_pair_mode(int64_t B, int K);
 /* How a call of this shape runs: 1 = ONE resident kernel (all rows of exp(S/eps) fit the SMs' shared memory);
  * 2 = ONE hybrid kernel (as many rows resident as fit, the rest re-read and re-exponentiated every iteration -- e.g.
  * BASELINE configs[2] at 2 / 4 GPUs); 0 = one streaming launch per pass (K % 4 != 0, K > 512, TIMET_SK_STREAMING=1). */

@@ -37,6 +37,7 @@ _PROTOS = {
     "timet_sinkhorn": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "timet_sinkhorn_ex": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "timet_sinkhorn_pair": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "timet_sinkhorn_pair_mode": (C.c_int, [C.c_int64, C.c_int]),
     "timet_sinkhorn_resident": (C.c_int, [C.c_int64, C.c_int]),
     "timet_cosine_scores_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "timet_cosine_scores": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),

@@ -954,6 +954,16 @@ int timet_sinkhorn_resident(int64_t B, int K) {
     return 0;
 }
 
+int timet_sinkhorn_pair_mode(int64_t B, int K) {
+    const EnvCfg &E = env_cfg();
+    int g, rpc, res;
+    size_t smem;
+    if (B < 1 || K < 1 || E.sk_streaming) return 0;
+    if (!E.sk_pair && !E.sk_no_dual && sk_hybrid_plan(B, K, &g, &rpc, &res, &smem, num_sms() / 2) && g <= 160) return 1;
+    if (E.sk_pair && sk_pair_plan(B, K, &g, &rpc, &smem) && g <= 160) return 2;
+    return 0;
+}
+
 int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float epsilon, int iters, int world_size,
                       timet_comm_t comm, float *q_out, const timet_sinkhorn_opts *opts, void *workspace, size_t workspace_bytes,
                       timet_stream_t stream) {

@@ -140,6 +140,11 @@ def sinkhorn_mode(B: int, K: int) -> str:
     return ("streaming", "resident", "hybrid")[int(_cabi.lib().timet_sinkhorn_resident(int(B), int(K)))]
 
 
+def sinkhorn_pair_mode(B: int, K: int) -> str:
+    """How sinkhorn_pair_from_scores runs: "dual" (one launch, the two problems side by side), "interleaved" or "sequential"."""
+    return ("sequential", "dual", "interleaved")[int(_cabi.lib().timet_sinkhorn_pair_mode(int(B), int(K)))]
+
+
 def sinkhorn_is_resident(B: int, K: int) -> bool:
     return sinkhorn_mode(B, K) == "resident"
 

@@ -69,6 +69,7 @@ class StepRunner:
         self.q_tgt = torch.empty((bs, self.N, K), dtype=torch.float32, device=self.device)
         self.sinkhorn_mode = ops.sinkhorn_mode(bs * self.N, K)
         self.sinkhorn_resident = self.sinkhorn_mode == "resident"
+        self.sinkhorn_pair_mode = ops.sinkhorn_pair_mode(bs * self.N, K)
         # the choreography above needs the one-launch resident Sinkhorn kernel and the tensor-core engine's event hook
         self.overlap = bool(overlap) and self.sinkhorn_resident and engine != ops.FF_EXACT and self.plan.tc_supported
         with torch.cuda.device(self.device):
