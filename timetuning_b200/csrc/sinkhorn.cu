@@ -378,6 +378,95 @@ __device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long l
     __syncthreads();
 }
 
+// Packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2 / FFMA2 issue one instruction for two IEEE fp32 operations): the sweep is
+// issue-bound, so the multiply / accumulate work of a row is done on float2 halves of each float4.
+__device__ __forceinline__ float2 lo2(const float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4 v) { return make_float2(v.z, v.w); }
+
+// One sweep over `nrows` rows (warp `warp` takes rows warp, warp + WARPS, ...; two rows in flight):
+//   s_j = sum_i a_i E_ji;   not last: acc_i += a_i E_ji * c / s_j   (marginals of the next Q);   last: Q_ji = a_i E_ji / s_j
+// RESIDENT: E read from shared memory; else re-read from global memory and re-exponentiated (bit-identical values).
+// Row sum order (canonical for every kernel of this file): per float4 ((x + z) + (y + w)), float4 chunks in lane order,
+// then the xor butterfly.
+template <int NV4, int WARPS, bool RESIDENT, bool ZERO = true>
+__device__ __forceinline__ void skp_sweep(const SkResArgs &A, const float4 *E, int64_t row0, int nrows, const float *a_s,
+                                          float4 (&acc)[NV4], bool last, int warp, int lane) {
+    const int K = A.K, K4 = K >> 2;
+    float4 av[NV4];
+#pragma unroll
+    for (int v = 0; v < NV4; ++v) {
+        const int i4 = lane + 32 * v;
+        av[v] = (i4 < K4) ? reinterpret_cast<const float4 *>(a_s)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ZERO) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    constexpr int RPW = (NV4 <= 2) ? 2 : 1;           // wider rows (K > 256) would spill with two rows in registers
+    for (int rl = warp; rl < nrows; rl += RPW * WARPS) {
+        const int rl2 = rl + WARPS;
+        const bool two = RPW == 2 && rl2 < nrows;
+        float2 pl[NV4], ph[NV4], ql[NV4], qh[NV4];
+        float s = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV4; ++v) {
+            const int i4 = lane + 32 * v;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f), f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RESIDENT) {
+                if (i4 < K4) e = E[(size_t)rl * K4 + i4];
+                if (two && i4 < K4) f = E[(size_t)rl2 * K4 + i4];
+            } else {
+                if (i4 < K4) e = __ldg(reinterpret_cast<const float4 *>(A.in + (row0 + rl) * K) + i4);
+                if (two && i4 < K4) f = __ldg(reinterpret_cast<const float4 *>(A.in + (row0 + rl2) * K) + i4);
+                if (A.scores_mode) {
+                    if (i4 < K4) {
+                        e.x = expf(e.x * A.inv_eps); e.y = expf(e.y * A.inv_eps); e.z = expf(e.z * A.inv_eps); e.w = expf(e.w * A.inv_eps);
+                    }
+                    if (two && i4 < K4) {
+                        f.x = expf(f.x * A.inv_eps); f.y = expf(f.y * A.inv_eps); f.z = expf(f.z * A.inv_eps); f.w = expf(f.w * A.inv_eps);
+                    }
+                }
+            }
+            pl[v] = __fmul2_rn(lo2(e), lo2(av[v])); ph[v] = __fmul2_rn(hi2(e), hi2(av[v]));
+            ql[v] = __fmul2_rn(lo2(f), lo2(av[v])); qh[v] = __fmul2_rn(hi2(f), hi2(av[v]));
+            const float2 t = __fadd2_rn(pl[v], ph[v]), t2 = __fadd2_rn(ql[v], qh[v]);
+            s += t.x + t.y;
+            s2 += t2.x + t2.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (!last) {
+            const float b = __fdiv_rn(A.c, s);
+            const float b2 = two ? __fdiv_rn(A.c, s2) : 0.f;
+            const float2 bb = make_float2(b, b), bb2 = make_float2(b2, b2);
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                float2 al = __ffma2_rn(pl[v], bb, lo2(acc[v])), ah = __ffma2_rn(ph[v], bb, hi2(acc[v]));
+                if (two) { al = __ffma2_rn(ql[v], bb2, al); ah = __ffma2_rn(qh[v], bb2, ah); }
+                acc[v] = make_float4(al.x, al.y, ah.x, ah.y);
+            }
+        } else {
+            const float inv = __fdiv_rn(1.f, s);
+            const float inv2 = two ? __fdiv_rn(1.f, s2) : 0.f;
+            const float2 ii = make_float2(inv, inv), ii2 = make_float2(inv2, inv2);
+            float4 *dst = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + rl, K, A.out_block_rows, A.out_block_stride));
+            float4 *dst2 = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + (two ? rl2 : rl), K, A.out_block_rows, A.out_block_stride));
+#pragma unroll
+            for (int v = 0; v < NV4; ++v) {
+                const int i4 = lane + 32 * v;
+                if (i4 < K4) {
+                    const float2 a = __fmul2_rn(pl[v], ii), bq = __fmul2_rn(ph[v], ii);
+                    __stcs(dst + i4, make_float4(a.x, a.y, bq.x, bq.y));
+                }
+                if (two && i4 < K4) {
+                    const float2 a = __fmul2_rn(ql[v], ii2), bq = __fmul2_rn(qh[v], ii2);
+                    __stcs(dst2 + i4, make_float4(a.x, a.y, bq.x, bq.y));
+                }
+            }
+        }
+    }
+}
+
 template <int NV4, int SKR_THREADS>
 __global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_resident(SkResArgs A) {   // <= 64 registers either way
     constexpr int SKR_WARPS = SKR_THREADS / 32;
@@ -430,66 +519,9 @@ __global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_re
 
     unsigned long long prev0 = 0ull, prev1 = 0ull;                    // accumulator values read at the previous even / odd iteration
     for (int it = 0; it < A.iters; ++it) {
-        float4 av[NV4];
-#pragma unroll
-        for (int v = 0; v < NV4; ++v) {
-            const int i4 = lane + 32 * v;
-            av[v] = (i4 < K4) ? reinterpret_cast<const float4 *>(a_s)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         const bool last = (it == A.iters - 1);
-        // ---- sweep the resident rows: s_j = sum_i a_i E_ji ; then either u_i += a_i E_ji * c/s_j or write Q.
-        // Two rows of a warp are in flight together (their load -> multiply -> butterfly -> divide chains are
-        // independent); rows still enter acc in ascending order, so the sums are the same bit for bit.
-        constexpr int RPW = (NV4 <= 2) ? 2 : 1;           // wider rows (K > 256) would spill with two rows in registers
-        for (int rl = warp; rl < nrows; rl += RPW * SKR_WARPS) {
-            const int rl2 = rl + SKR_WARPS;
-            const bool two = RPW == 2 && rl2 < nrows;
-            float4 p[NV4], q[NV4];
-            float s = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int v = 0; v < NV4; ++v) {
-                const int i4 = lane + 32 * v;
-                const float4 e = (i4 < K4) ? E[(size_t)rl * K4 + i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 f = (two && i4 < K4) ? E[(size_t)rl2 * K4 + i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-                p[v] = make_float4(e.x * av[v].x, e.y * av[v].y, e.z * av[v].z, e.w * av[v].w);
-                q[v] = make_float4(f.x * av[v].x, f.y * av[v].y, f.z * av[v].z, f.w * av[v].w);
-                s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
-                s2 += (q[v].x + q[v].y) + (q[v].z + q[v].w);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if (!last) {
-                const float b = __fdiv_rn(A.c, s);
-                const float b2 = two ? __fdiv_rn(A.c, s2) : 0.f;
-#pragma unroll
-                for (int v = 0; v < NV4; ++v) {
-                    acc[v].x = fmaf(p[v].x, b, acc[v].x); acc[v].y = fmaf(p[v].y, b, acc[v].y);
-                    acc[v].z = fmaf(p[v].z, b, acc[v].z); acc[v].w = fmaf(p[v].w, b, acc[v].w);
-                }
-                if (two) {
-#pragma unroll
-                    for (int v = 0; v < NV4; ++v) {
-                        acc[v].x = fmaf(q[v].x, b2, acc[v].x); acc[v].y = fmaf(q[v].y, b2, acc[v].y);
-                        acc[v].z = fmaf(q[v].z, b2, acc[v].z); acc[v].w = fmaf(q[v].w, b2, acc[v].w);
-                    }
-                }
-            } else {
-                const float inv = __fdiv_rn(1.f, s);
-                const float inv2 = two ? __fdiv_rn(1.f, s2) : 0.f;
-                float4 *dst = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + rl, K, A.out_block_rows, A.out_block_stride));
-                float4 *dst2 = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + (two ? rl2 : rl), K, A.out_block_rows, A.out_block_stride));
-#pragma unroll
-                for (int v = 0; v < NV4; ++v) {
-                    const int i4 = lane + 32 * v;
-                    if (i4 < K4) __stcs(dst + i4, make_float4(p[v].x * inv, p[v].y * inv, p[v].z * inv, p[v].w * inv));
-                    if (two && i4 < K4) __stcs(dst2 + i4, make_float4(q[v].x * inv2, q[v].y * inv2, q[v].z * inv2, q[v].w * inv2));
-                }
-            }
-        }
+        // ---- sweep the resident rows (skp_sweep): s_j = sum_i a_i E_ji ; then either u_i += a_i E_ji * c/s_j or write Q
+        skp_sweep<NV4, SKR_WARPS, true>(A, E, row0, nrows, a_s, acc, last, warp, lane);
         if (last) break;
         // ---- marginals of Q itself, u_i = sum_j a_i E_ji b_j (they sum to 1 over i, so the fixed point never
         // overflows): integer atomics are associative -> the grid-wide sum is bit-reproducible without a fold.
@@ -547,82 +579,6 @@ __global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_re
 struct SkPairArgs {
     SkResArgs a[2];           // per-problem pointers / accumulators (shape fields equal); a[0] is the resident one
 };
-
-template <int NV4, int WARPS, bool RESIDENT, bool ZERO = true>
-__device__ __forceinline__ void skp_sweep(const SkResArgs &A, const float4 *E, int64_t row0, int nrows, const float *a_s,
-                                          float4 (&acc)[NV4], bool last, int warp, int lane) {
-    const int K = A.K, K4 = K >> 2;
-    float4 av[NV4];
-#pragma unroll
-    for (int v = 0; v < NV4; ++v) {
-        const int i4 = lane + 32 * v;
-        av[v] = (i4 < K4) ? reinterpret_cast<const float4 *>(a_s)[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ZERO) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    constexpr int RPW = (NV4 <= 2) ? 2 : 1;
-    for (int rl = warp; rl < nrows; rl += RPW * WARPS) {
-        const int rl2 = rl + WARPS;
-        const bool two = RPW == 2 && rl2 < nrows;
-        float4 p[NV4], q[NV4];
-        float s = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int v = 0; v < NV4; ++v) {
-            const int i4 = lane + 32 * v;
-            float4 e = make_float4(0.f, 0.f, 0.f, 0.f), f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (RESIDENT) {
-                if (i4 < K4) e = E[(size_t)rl * K4 + i4];
-                if (two && i4 < K4) f = E[(size_t)rl2 * K4 + i4];
-            } else {
-                if (i4 < K4) e = __ldg(reinterpret_cast<const float4 *>(A.in + (row0 + rl) * K) + i4);
-                if (two && i4 < K4) f = __ldg(reinterpret_cast<const float4 *>(A.in + (row0 + rl2) * K) + i4);
-                if (A.scores_mode) {
-                    if (i4 < K4) {
-                        e.x = expf(e.x * A.inv_eps); e.y = expf(e.y * A.inv_eps); e.z = expf(e.z * A.inv_eps); e.w = expf(e.w * A.inv_eps);
-                    }
-                    if (two && i4 < K4) {
-                        f.x = expf(f.x * A.inv_eps); f.y = expf(f.y * A.inv_eps); f.z = expf(f.z * A.inv_eps); f.w = expf(f.w * A.inv_eps);
-                    }
-                }
-            }
-            p[v] = make_float4(e.x * av[v].x, e.y * av[v].y, e.z * av[v].z, e.w * av[v].w);
-            q[v] = make_float4(f.x * av[v].x, f.y * av[v].y, f.z * av[v].z, f.w * av[v].w);
-            s += (p[v].x + p[v].y) + (p[v].z + p[v].w);
-            s2 += (q[v].x + q[v].y) + (q[v].z + q[v].w);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        if (!last) {
-            const float b = __fdiv_rn(A.c, s);
-            const float b2 = two ? __fdiv_rn(A.c, s2) : 0.f;
-#pragma unroll
-            for (int v = 0; v < NV4; ++v) {
-                acc[v].x = fmaf(p[v].x, b, acc[v].x); acc[v].y = fmaf(p[v].y, b, acc[v].y);
-                acc[v].z = fmaf(p[v].z, b, acc[v].z); acc[v].w = fmaf(p[v].w, b, acc[v].w);
-            }
-            if (two) {
-#pragma unroll
-                for (int v = 0; v < NV4; ++v) {
-                    acc[v].x = fmaf(q[v].x, b2, acc[v].x); acc[v].y = fmaf(q[v].y, b2, acc[v].y);
-                    acc[v].z = fmaf(q[v].z, b2, acc[v].z); acc[v].w = fmaf(q[v].w, b2, acc[v].w);
-                }
-            }
-        } else {
-            const float inv = __fdiv_rn(1.f, s);
-            const float inv2 = two ? __fdiv_rn(1.f, s2) : 0.f;
-            float4 *dst = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + rl, K, A.out_block_rows, A.out_block_stride));
-            float4 *dst2 = reinterpret_cast<float4 *>(sk_out_row(A.q_out, row0 + (two ? rl2 : rl), K, A.out_block_rows, A.out_block_stride));
-#pragma unroll
-            for (int v = 0; v < NV4; ++v) {
-                const int i4 = lane + 32 * v;
-                if (i4 < K4) __stcs(dst + i4, make_float4(p[v].x * inv, p[v].y * inv, p[v].z * inv, p[v].w * inv));
-                if (two && i4 < K4) __stcs(dst2 + i4, make_float4(q[v].x * inv2, q[v].y * inv2, q[v].z * inv2, q[v].w * inv2));
-            }
-        }
-    }
-}
 
 // P: fold the CTA's marginal partials and add them (with the arrival) to the grid-wide fixed-point accumulators
 template <int NV4, int WARPS>
