@@ -50,6 +50,7 @@ struct EnvCfg {
     int tc_pflags, tc_flags, tc_stages, tc_nbuf, tc_clip_group;   // 0 = default
     bool tc_pair, tc_persist, tc_dyn, tc_trace;
     bool sk_streaming, sk_pair, sk_no_dual;
+    int sk_ll;                                                     // 1 (default): tagged-word NVLink exchange; 0: data + flag
     int sk_ustride;                                                // 0 = default
     int sc_stages;                                                 // cosine-scores GEMM ring depth (2 = two CTAs per SM, default; 4)
     int gather_batch;                                              // gather: label rows in flight per batch (0 = by topk)
@@ -66,6 +67,9 @@ struct P2PBuf {
     unsigned long long flag[P2P_MAX_RANKS];          // flag[src] = number of exchanges src has published here
     unsigned long long pad[16];
     float slot[3][P2P_MAX_RANKS][P2P_MAX_K];         // slot[e % 3][src] = src's K-vector of exchange e
+    // low-latency form: one 8-byte word per value = (float bits, exchange number + 1).  The tag travels WITH the data in one
+    // single-copy-atomic store, so no separate flag + release fence (one NVLink latency per exchange instead of two).
+    unsigned long long ll[3][P2P_MAX_RANKS][P2P_MAX_K];
 };
 // *epoch points at the two per-channel exchange counters (every rank's buffer is P2PBuf[2])
 bool comm_p2p_info(timet_comm_t comm, void ***peers_dev, int *rank, int *ws, unsigned long long **epoch);

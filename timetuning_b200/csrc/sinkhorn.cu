@@ -278,6 +278,7 @@ struct SkResArgs {
     void *const *peers;       // world_size > 1: every rank's P2PBuf[2] (NVLink peer memory), else nullptr
     int rank, ws;
     int chan;                 // exchange channel (P2PBuf index): two problems running side by side use one each
+    int ll;                   // 1: low-latency tagged-word exchange (default), 0: data + flag with release / acquire
     int g_first, g_size;      // CTAs [g_first, g_first + g_size) of the launch work on this problem (0 / 0 = the whole grid)
     unsigned long long epoch0; // exchanges completed before this call (same on every rank)
     unsigned long long timeout_ns; // patience of the in-kernel waits (env TIMET_P2P_TIMEOUT_S, default 10 min)
@@ -332,8 +333,55 @@ __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[N
 // the world_size vectors in rank order (bit-identical on all ranks).  `vec` (shared memory, [K]) holds the local
 // vector on entry and the global sum on exit.  A slot is reused after 3 exchanges; a peer can only be one exchange
 // ahead, so it is never overwritten while still being read.
+// Low-latency exchange (default): every value is sent as ONE 8-byte word (float bits | tag = exchange number + 1 in the
+// high half).  The leader CTA of the problem stores the rank's K words into every rank's buffer; every CTA of every rank
+// polls the K x world_size words of its own buffer until their tags match and adds the values in rank order.  An 8-byte
+// store is single-copy atomic, so data and "flag" arrive together: no fence, no second round trip.  (32-bit non-zero
+// tags; a slot is reused every 3 exchanges, so a stale word can never carry the awaited tag.)
 template <int SKR_THREADS>
-__device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long long e, float *vec) {
+__device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned long long e, float *vec) {
+    const int K = A.K;
+    P2PBuf *own = reinterpret_cast<P2PBuf *>(A.peers[A.rank]) + A.chan;
+    const int slot = (int)(e % 3ull);
+    const unsigned long long tag = ((e % 0xFFFFFFFFull) + 1ull) << 32;      // never 0: a zero-initialised buffer matches nothing
+    if ((int)blockIdx.x == A.g_first) {
+        for (int idx = threadIdx.x; idx < K * A.ws; idx += SKR_THREADS) {
+            const int p = idx / K, i = idx - p * K;
+            unsigned long long *dst = &(reinterpret_cast<P2PBuf *>(A.peers[p]) + A.chan)->ll[slot][A.rank][i];
+            const unsigned long long word = tag | (unsigned long long)__float_as_uint(vec[i]);
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+        }
+    }
+    __syncthreads();                                   // vec is rewritten below
+    for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
+        float t = 0.f;
+        for (int r = 0; r < A.ws; ++r) {
+            const unsigned long long *src = &own->ll[slot][r][i];
+            unsigned long long v, t0 = 0ull;
+            unsigned int spins = 0;
+            do {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                if ((v & 0xFFFFFFFF00000000ull) == tag) break;
+                if ((++spins & 0xFFFu) == 0u) {
+                    const unsigned long long now = globaltimer_ns();
+                    if (t0 == 0ull) t0 = now;
+                    else if (now - t0 > A.timeout_ns) {
+                        printf("timet: sinkhorn peer exchange timed out after %llu s (rank %d waiting for rank %d, exchange %llu)\n",
+                               A.timeout_ns / 1000000000ull, A.rank, r, e);
+                        __trap();
+                    }
+                    __nanosleep(100);
+                }
+            } while (true);
+            t += __uint_as_float((unsigned int)(v & 0xFFFFFFFFull));
+        }
+        vec[i] = t;
+    }
+    __syncthreads();
+}
+
+template <int SKR_THREADS>
+__device__ __forceinline__ void skr_exchange_flag(const SkResArgs &A, unsigned long long e, float *vec) {
     const int K = A.K;
     P2PBuf *own = reinterpret_cast<P2PBuf *>(A.peers[A.rank]) + A.chan;
     const int slot = (int)(e % 3ull);
@@ -376,6 +424,12 @@ __device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long l
         vec[i] = t;
     }
     __syncthreads();
+}
+
+template <int SKR_THREADS>
+__device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long long e, float *vec) {
+    if (A.ll) skr_exchange_ll<SKR_THREADS>(A, e, vec);
+    else skr_exchange_flag<SKR_THREADS>(A, e, vec);
 }
 
 // Packed fp32x2 arithmetic (sm_100: FMUL2 / FADD2 / FFMA2 issue one instruction for two IEEE fp32 operations): the sweep is
@@ -959,7 +1013,7 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
             const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;   // 1 = packed accumulators (for comparison)
             TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
             SkResArgs R;
-            R.chan = 0; R.g_first = 0; R.g_size = 0;
+            R.chan = 0; R.g_first = 0; R.g_size = 0; R.ll = E.sk_ll;
             R.ustride = ustride;
             // 48 data bits: the marginals of one iteration sum to <= 1 and a buffer accumulates ceil(iters / 2) of them
             int head = 1;
@@ -996,7 +1050,7 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
             TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
             SkPairArgs HP;
             SkResArgs &R = HP.a[0];
-            R.chan = 0; R.g_first = 0; R.g_size = hgrid;
+            R.chan = 0; R.g_first = 0; R.g_size = hgrid; R.ll = E.sk_ll;
             R.ustride = ustride;
             int head = 1;
             while ((1 << head) < iters / 2 + 2) ++head;
@@ -1114,7 +1168,7 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
             for (int c = 0; c < 2; ++c) {
                 TIMET_CUDA(cudaMemsetAsync(wsp[c] + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
                 SkResArgs &R = P.a[c];
-                R.chan = c; R.g_first = c * dgrid; R.g_size = dgrid;
+                R.chan = c; R.g_first = c * dgrid; R.g_size = dgrid; R.ll = E.sk_ll;
                 R.ustride = ustride;
                 R.ufix_scale = ldexpf(1.0f, 47 - head);
                 R.ufix_inv = ldexpf(1.0f, head - 47);
@@ -1152,7 +1206,7 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
     for (int c = 0; c < 2; ++c) {
         TIMET_CUDA(cudaMemsetAsync(wsp[c] + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
         SkResArgs &R = P.a[c];
-        R.chan = 0; R.g_first = 0; R.g_size = 0;
+        R.chan = 0; R.g_first = 0; R.g_size = 0; R.ll = E.sk_ll;
         R.ustride = ustride;
         R.ufix_scale = ldexpf(1.0f, 47 - head);
         R.ufix_inv = ldexpf(1.0f, head - 47);
