@@ -95,7 +95,7 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
                         int world_size, timet_comm_t comm, float *q0, const timet_sinkhorn_opts *opts0, float *q1,
                         const timet_sinkhorn_opts *opts1, void *workspace, size_t workspace_bytes, timet_stream_t stream);
 /* How timet_sinkhorn_pair runs this shape: 1 = DUAL (one launch, the two problems side by side on half of the SMs each:
- * the default), 2 = interleaved on the whole grid (TIMET_SK_PAIR=1), 0 = two timet_sinkhorn_ex calls one after the other */
+ * the default), 0 = two timet_sinkhorn_ex calls one after the other (TIMET_SK_DUAL=0, K % 4 != 0, K > 512) */
 int timet_sinkhorn_pair_mode(int64_t B, int K);
 /* How a call of this shape runs: 1 = ONE resident kernel (all rows of exp(S/eps) fit the SMs' shared memory);
  * 2 = ONE hybrid kernel (as many rows resident as fit, the rest re-read and re-exponentiated every iteration -- e.g.

@@ -38,8 +38,6 @@ VARIANTS = (("persistent", {}), ("static-schedule", {"TIMET_TC_DYN": "0"}), ("ol
             ("scan-noappend", {"TIMET_TC_PFLAGS": "2"}), ("tmem-loads-only", {"TIMET_TC_PFLAGS": "4"}),
             ("per-tile", {"TIMET_TC_PERSIST": "0"}), ("per-tile-mma-only", {"TIMET_TC_PERSIST": "0", "TIMET_TC_FLAGS": "1"}),
             ("per-tile-noappend", {"TIMET_TC_PERSIST": "0", "TIMET_TC_FLAGS": "2"}),
-            ("pair", {"TIMET_TC_PAIR": "1"}), ("pair-mma-only", {"TIMET_TC_PAIR": "1", "TIMET_TC_FLAGS": "1"}),
-            ("pair-noappend", {"TIMET_TC_PAIR": "1", "TIMET_TC_FLAGS": "2"}),
             ("stages-2", {"TIMET_TC_STAGES": "2"}), ("mma-only-stages-2", {"TIMET_TC_PFLAGS": "1", "TIMET_TC_STAGES": "2"}))
 for name, extra in VARIANTS:
     if len(sys.argv) > 1 and name not in sys.argv[1:]:

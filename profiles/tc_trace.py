@@ -21,7 +21,7 @@ plan.prepare(feats)
 for _ in range(3):
     plan.select(tb.FF_TC)
 torch.cuda.synchronize()
-n = min(4096, bs * 7 * (8 if os.environ.get('TIMET_TC_PAIR') == '1' else 7))
+n = min(4096, bs * 7 * 7)
 out = torch.zeros((n, 8), dtype=torch.int64, device="cuda")
 _cabi.check(_cabi.lib().timet_debug_tc_trace(C.byref(plan.params), _ptr(plan.workspace), plan.nbytes, _ptr(out), n, _stream()), "trace")
 t = out.cpu().numpy().astype(np.float64)

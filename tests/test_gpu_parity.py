@@ -390,8 +390,8 @@ def test_sinkhorn_rows_beyond_shared_memory():
 def test_sinkhorn_pair_is_two_single_calls(timet_env, B, K, iters):
     """timet_sinkhorn_pair: the source and target assignment of a step in ONE launch.  Default = DUAL (the two problems
     side by side on half of the SMs each: same maths, another row partition -> equal to two single calls within fp32
-    summation order, bit-reproducible); TIMET_SK_DUAL=0 = one after the other and TIMET_SK_PAIR=1 = interleaved on the whole
-    grid, both bit-identical to two single calls; K = 516 exercises the sequential fall-back."""
+    summation order, bit-reproducible); TIMET_SK_DUAL=0 = one after the other, bit-identical to two single calls; K = 516
+    exercises the sequential fall-back."""
     s0, s1 = cu(synth.cosine_scores(B, K, seed=5)), cu(synth.cosine_scores(B, K, seed=6))
     r0, r1 = tb.sinkhorn_from_scores(s0, 0.05, iters), tb.sinkhorn_from_scores(s1, 0.05, iters)
     d0, d1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)           # default: dual
@@ -402,10 +402,7 @@ def test_sinkhorn_pair_is_two_single_calls(timet_env, B, K, iters):
     assert_close(d1.cpu().numpy(), O.sinkhorn_scaling(s1.cpu().numpy(), 0.05, iters, dtype=np.float64), what="dual vs fp64 oracle")
     timet_env(TIMET_SK_DUAL="0")
     q0, q1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
-    assert torch.equal(q0, r0) and torch.equal(q1, r1)
-    timet_env(TIMET_SK_DUAL="0", TIMET_SK_PAIR="1")
-    q0, q1 = tb.sinkhorn_pair_from_scores(s0, s1, 0.05, iters)
-    timet_env(TIMET_SK_DUAL=None, TIMET_SK_PAIR=None)
+    timet_env(TIMET_SK_DUAL=None)
     assert torch.equal(q0, r0) and torch.equal(q1, r1), ((q0 - r0).abs().max().item(), (q1 - r1).abs().max().item())
 
 

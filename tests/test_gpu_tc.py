@@ -132,7 +132,6 @@ def test_tc_random_features_worst_case():
 
 @pytest.mark.parametrize("env", [
     {"TIMET_TC_PERSIST": "0"},                  # one CTA per work item (ff_tc.cu)
-    {"TIMET_TC_PAIR": "1"},                     # CTA pairs, cta_group::2 (ff_tc2.cu)
     {"TIMET_TC_DYN": "0"},                      # persistent kernel, static snake schedule
     {"TIMET_TC_NBUF": "4"},                     # four 128-column TMEM buffers
     {"TIMET_TC_PFLAGS": "128"},                 # every TMEM buffer scanned by its own two groups

@@ -20,7 +20,7 @@ LIB = os.path.join(LIBDIR, "libtimet_b200.so")
 STAMP = os.path.join(LIBDIR, "build.stamp")
 
 SOURCES = ["common.cu", "sinkhorn.cu", "comm.cu", "misc.cu", "ff_prepare.cu", "ff_select_exact.cu",
-           "ff_gather.cu", "ff_tc.cu", "ff_tc2.cu", "ff_tc3.cu", "scores.cu", "ff_api.cu"]
+           "ff_gather.cu", "ff_tc.cu", "ff_tc3.cu", "scores.cu", "ff_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-diag-suppress", "128"]
 

@@ -43,14 +43,12 @@ void env_reload() {
     e.tc_stages = env_int("TIMET_TC_STAGES", 0);
     e.tc_nbuf = env_int("TIMET_TC_NBUF", 0);
     e.tc_clip_group = env_int("TIMET_TC_CLIP_GROUP", 0);
-    e.tc_pair = env_int("TIMET_TC_PAIR", 0) == 1;
     e.tc_persist = env_int("TIMET_TC_PERSIST", 1) != 0;
     e.tc_dyn = env_int("TIMET_TC_DYN", 1) != 0;
     e.tc_trace = env_int("TIMET_TC_TRACE", 0) == 1;
     e.sk_streaming = env_int("TIMET_SK_STREAMING", 0) == 1;
     e.sk_no_dual = env_int("TIMET_SK_DUAL", 1) == 0;     // 0: the two calls of timet_sinkhorn_pair one after the other
     e.sk_ll = env_int("TIMET_SK_LL", 1) != 0 ? 1 : 0;
-    e.sk_pair = env_int("TIMET_SK_PAIR", 0) == 1;     // measured slower than two single calls at configs[1] (0.141 vs 0.135 ms)
     e.sk_ustride = env_int("TIMET_SK_USTRIDE", 0);
     e.fin_batch = env_int("TIMET_FIN_BATCH", 0);
     e.gather_batch = env_int("TIMET_GATHER_BATCH", 0);

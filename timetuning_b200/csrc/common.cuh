@@ -48,8 +48,8 @@ int num_sms();
 // timet_debug_reload_env() re-reads them (tests flip switches inside one process).
 struct EnvCfg {
     int tc_pflags, tc_flags, tc_stages, tc_nbuf, tc_clip_group;   // 0 = default
-    bool tc_pair, tc_persist, tc_dyn, tc_trace;
-    bool sk_streaming, sk_pair, sk_no_dual;
+    bool tc_persist, tc_dyn, tc_trace;
+    bool sk_streaming, sk_no_dual;
     int sk_ll;                                                     // 1 (default): tagged-word NVLink exchange; 0: data + flag
     int sk_ustride;                                                // 0 = default
     int sc_stages;                                                 // cosine-scores GEMM ring depth (2 = two CTAs per SM, default; 4)

@@ -28,7 +28,7 @@
 //               single-pass compaction raises the nomination threshold, which the groups of a query share through
 //               an atomicMax word in shared memory; at the end the four lists are filtered with the final
 //               threshold, merged and <= 16 candidates per query are published.
-// ff_tc2.cu holds the CTA-pair (cta_group::2) variant of the same kernel.
+// (A CTA-pair cta_group::2 variant was measured slower twice and removed in round 2: profiles/r2_experiments.md.)
 #include <stdlib.h>
 
 #include "ff_tc_dev.cuh"
@@ -583,7 +583,6 @@ bool ff_tc_supported(const timet_ff_params &p) {
 int ff_select_exact_run(const timet_ff_params &p, const FFLayout &L, const float *feats, char *ws, const int32_t *qlist,
                         const unsigned int *qcount, int64_t max_items, cudaStream_t st);
 
-int ff_select_tc_pair_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
 int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st);
 
 // optional CUDA events recorded on the stream right before / after the nomination (tensor-core) kernel, so a
@@ -600,10 +599,8 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float
     uint32_t *cand = reinterpret_cast<uint32_t *>(ws + L.off_cand);
     uint32_t *meta = reinterpret_cast<uint32_t *>(ws + L.off_cand_meta);
     if (g_ev_nominate_begin) TIMET_CUDA(cudaEventRecord(g_ev_nominate_begin, st));
-    // nomination: 1-CTA kernel by default; TIMET_TC_PAIR=1 selects the CTA-pair kernel (cta_group::2, ff_tc2.cu)
     const EnvCfg &E = env_cfg();
-    rc = E.tc_pair ? ff_select_tc_pair_launch(p, L, ws, st) : TIMET_ERR_UNSUPPORTED;   // opt-in
-    if (rc != TIMET_OK && rc != TIMET_ERR_UNSUPPORTED) return rc;
+    rc = TIMET_ERR_UNSUPPORTED;
     if (rc == TIMET_ERR_UNSUPPORTED) {
         // persistent kernel (ff_tc3.cu): one CTA per SM walks the work items; TIMET_TC_PERSIST=0 selects the per-tile kernel
         const bool debug = E.tc_trace || E.tc_flags != 0;

@@ -1,4 +1,4 @@
-// Device-side building blocks shared by the 1-CTA (ff_tc.cu) and the CTA-pair (ff_tc2.cu) variants of the FF
+// Device-side building blocks shared by the per-item (ff_tc.cu) and the persistent (ff_tc3.cu) forms of the FF
 // tensor-core kernel: geometry, shared-memory control block, packed candidate lists, predicated offer,
 // warp-synchronous compaction.
 #pragma once

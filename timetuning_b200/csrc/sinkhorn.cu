@@ -620,16 +620,7 @@ __global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_re
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// PAIR variant: TWO Sinkhorn problems of the same shape in ONE resident launch (the source and the target assignment of a
-// training step, time_tuning.py:268,275).  A single call spends more than half of every iteration waiting for its
-// grid-wide reduction (atomic -> L2 -> poll) -- with two independent problems in one kernel each CTA sweeps one problem
-// while the other's reduction is in flight:
-//     S(A,0) P(A,0) | S(B,it) P(B,it)  W(A,it)  S(A,it+1) P(A,it+1)  W(B,it) | ...        S sweep, P post, W wait + update
-// Problem A keeps exp(S/eps) resident in shared memory like sk_resident; both do not fit (2 x 136 KB at config 2), so
-// problem B's rows are re-read from L2 (the 20 MB score matrix stays L2-resident) and re-exponentiated every iteration
-// -- bit-identical values, and the extra L2 traffic rides under A's reduction latency.  The arithmetic per problem is
-// the one of sk_resident<.., 1024> in the same order, so a pair call returns the same bits as two single calls.
+// Arguments of a launch that works on one or two problems (sk_hybrid).
 struct SkPairArgs {
     SkResArgs a[2];           // per-problem pointers / accumulators (shape fields equal); a[0] is the resident one
 };
@@ -683,102 +674,6 @@ __device__ __forceinline__ void skp_wait(const SkResArgs &A, int it, unsigned lo
     if (A.ws > 1) skr_exchange<THREADS>(A, xch++, u_s);
     if (i < K) a_s[i] = a_s[i] * __fdiv_rn(A.r, u_s[i]);
     __syncthreads();
-}
-
-template <int NV4>
-__global__ void __launch_bounds__(1024, 1) sk_resident_pair(SkPairArgs P) {
-    constexpr int THREADS = 1024, WARPS = THREADS / 32;
-    extern __shared__ float4 smem4[];
-    const SkResArgs &A = P.a[0], &Bp = P.a[1];
-    const int K = A.K, K4 = K >> 2;
-    float4 *E = smem4;                                                              // [rows_per_cta, K4]: problem A
-    float *a_sA = reinterpret_cast<float *>(smem4 + (size_t)A.rows_per_cta * K4);   // [K]
-    float *a_sB = a_sA + K;                                                         // [K]
-    float *u_s = a_sB + K;                                                          // [K]
-    float *red = u_s + K;                                                           // [SKR_RED, K]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row0 = (int64_t)blockIdx.x * A.rows_per_cta;
-    const int nrows = (int)max((int64_t)0, min((int64_t)A.rows_per_cta, A.B - row0));
-
-    float4 acc[NV4];
-    // ---- pass 0 of both problems: column sums of E (A: exponentiate once into shared memory; B: streamed)
-    for (int c = 0; c < 2; ++c) {
-        const SkResArgs &X = P.a[c];
-#pragma unroll
-        for (int v = 0; v < NV4; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int rl = warp; rl < nrows; rl += WARPS) {
-            const float4 *src = reinterpret_cast<const float4 *>(X.in + (row0 + rl) * K);
-#pragma unroll
-            for (int v = 0; v < NV4; ++v) {
-                const int i4 = lane + 32 * v;
-                if (i4 < K4) {
-                    float4 e = __ldg(src + i4);
-                    if (X.scores_mode) {
-                        e.x = expf(e.x * X.inv_eps); e.y = expf(e.y * X.inv_eps);
-                        e.z = expf(e.z * X.inv_eps); e.w = expf(e.w * X.inv_eps);
-                    }
-                    if (c == 0) E[(size_t)rl * K4 + i4] = e;
-                    acc[v].x += e.x; acc[v].y += e.y; acc[v].z += e.z; acc[v].w += e.w;
-                }
-            }
-        }
-        skr_fold_warps<NV4, WARPS>(red, acc, K, K4, warp, lane);
-        for (int i = threadIdx.x; i < K; i += THREADS) {
-            float t = 0.f;
-#pragma unroll
-            for (int w = 0; w < SKR_RED; ++w) t += red[w * K + i];
-            X.partials[(size_t)blockIdx.x * K + i] = t;
-        }
-        __syncthreads();
-    }
-    grid_barrier(A.bar, gridDim.x);
-    unsigned long long xch = A.epoch0;
-    fold_partials<THREADS>(A.partials, gridDim.x, K, red, a_sA, 0.f);
-    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_sA);
-    fold_partials<THREADS>(Bp.partials, gridDim.x, K, red, a_sB, 0.f);
-    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_sB);
-    for (int i = threadIdx.x; i < K; i += THREADS) {
-        a_sA[i] = __fdiv_rn(A.r, a_sA[i]);
-        a_sB[i] = __fdiv_rn(A.r, a_sB[i]);
-    }
-    __syncthreads();
-
-    // ---- iterations, software-pipelined across the two problems
-    unsigned long long pA0 = 0ull, pA1 = 0ull, pB0 = 0ull, pB1 = 0ull;
-    const int n = A.iters;
-    skp_sweep<NV4, WARPS, true>(A, E, row0, nrows, a_sA, acc, n == 1, warp, lane);
-    if (n > 1) skp_post<NV4, WARPS>(A, 0, red, acc, warp, lane);
-    for (int it = 0; it < n; ++it) {
-        const bool last = (it == n - 1);
-        skp_sweep<NV4, WARPS, false>(Bp, nullptr, row0, nrows, a_sB, acc, last, warp, lane);
-        if (last) break;
-        skp_post<NV4, WARPS>(Bp, it, red, acc, warp, lane);
-        skp_wait<THREADS>(A, it, pA0, pA1, xch, a_sA, u_s);
-        skp_sweep<NV4, WARPS, true>(A, E, row0, nrows, a_sA, acc, it + 1 == n - 1, warp, lane);
-        if (it + 1 < n - 1) skp_post<NV4, WARPS>(A, it + 1, red, acc, warp, lane);
-        skp_wait<THREADS>(Bp, it, pB0, pB1, xch, a_sB, u_s);
-    }
-}
-
-static bool sk_pair_plan(int64_t B, int K, int *grid, int *rows_per_cta, size_t *smem) {
-    if (K % 4 != 0 || K > 128 * 3) return false;          // NV4 <= 3
-    const int g = num_sms();
-    const int64_t rpc = (B + g - 1) / g;
-    const size_t need = (size_t)rpc * K * 4 + (size_t)3 * K * 4 + (size_t)SKR_RED * K * 4;
-    if (need > 226 * 1024) return false;
-    *grid = (int)((B + rpc - 1) / rpc);
-    *rows_per_cta = (int)rpc;
-    *smem = need;
-    return true;
-}
-
-template <int NV4>
-static int sk_pair_launch(SkPairArgs &P, int grid, size_t smem, cudaStream_t st) {
-    TIMET_CUDA(cudaFuncSetAttribute(sk_resident_pair<NV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void *args[] = {&P};
-    TIMET_CUDA(cudaLaunchCooperativeKernel((const void *)sk_resident_pair<NV4>, dim3(grid), dim3(1024), args, smem, st));
-    launch_counter()++;
-    return TIMET_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -969,8 +864,7 @@ int timet_sinkhorn_pair_mode(int64_t B, int K) {
     int g, rpc, res;
     size_t smem;
     if (B < 1 || K < 1 || E.sk_streaming) return 0;
-    if (!E.sk_pair && !E.sk_no_dual && sk_hybrid_plan(B, K, &g, &rpc, &res, &smem, num_sms() / 2) && g <= 160) return 1;
-    if (E.sk_pair && sk_pair_plan(B, K, &g, &rpc, &smem) && g <= 160) return 2;
+    if (!E.sk_no_dual && sk_hybrid_plan(B, K, &g, &rpc, &res, &smem, num_sms() / 2) && g <= 160) return 1;
     return 0;
 }
 
@@ -1130,26 +1024,16 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
     const timet_sinkhorn_opts *op[2] = {opts0, opts1};
     char *wsp[2] = {(char *)workspace, (char *)workspace + one};
     const EnvCfg &E = env_cfg();
-    int rgrid, rpc;
-    size_t rsmem;
     void **peers = nullptr;
     int prank = 0, pws = 1;
     unsigned long long *pepoch = nullptr;
     const bool p2p = world_size > 1 && comm != nullptr && comm_p2p_info(comm, &peers, &prank, &pws, &pepoch) && pws == world_size && K <= P2P_MAX_K;
-    bool ok = (world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && E.sk_pair && epsilon > 0.f &&
-              (input_kind == TIMET_SK_EXP || input_kind == TIMET_SK_SCORES) && sk_pair_plan(B, K, &rgrid, &rpc, &rsmem) && rgrid <= 160 &&
-              (int64_t)(iters / 2 + 1) * rgrid < (1 << SKR_CNT_BITS);
-    for (int c = 0; c < 2 && ok; ++c) {
-        const int64_t obr = op[c] ? op[c]->out_block_rows : 0, obs = op[c] ? op[c]->out_block_stride : 0;
-        ok = (reinterpret_cast<uintptr_t>(in[c]) & 15) == 0 && (reinterpret_cast<uintptr_t>(qo[c]) & 15) == 0 && (obs % 4) == 0 &&
-             (obr <= 0 || (obs >= obr * K && B % obr == 0));
-    }
     // ---- DUAL: the two problems side by side on half of the SMs each (sk_hybrid with nprob = 2), default
     {
         int dgrid, drpc, dres;
         size_t dsmem;
         const int half = num_sms() / 2;
-        bool dual = (world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && !E.sk_pair && !E.sk_no_dual && epsilon > 0.f &&
+        bool dual = (world_size == 1 || p2p) && iters >= 1 && !E.sk_streaming && !E.sk_no_dual && epsilon > 0.f &&
                     (input_kind == TIMET_SK_EXP || input_kind == TIMET_SK_SCORES) && half >= 1 &&
                     sk_hybrid_plan(B, K, &dgrid, &drpc, &dres, &dsmem, half) && dgrid <= 160 &&
                     (int64_t)(iters / 2 + 1) * dgrid < (1 << SKR_CNT_BITS);
@@ -1192,41 +1076,10 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
             }
         }
     }
-    if (!ok) {      // not a resident pair: two independent calls (each validates its own arguments)
-        int rc = timet_sinkhorn_ex(in0, B, K, input_kind, epsilon, iters, world_size, comm, q0, opts0, wsp[0], one, stream);
-        if (rc != TIMET_OK) return rc;
-        return timet_sinkhorn_ex(in1, B, K, input_kind, epsilon, iters, world_size, comm, q1, opts1, wsp[1], one, stream);
-    }
-    SkPairArgs P;
-    const size_t bar_off = (size_t)322 * K * sizeof(float);
-    const size_t ufix_off = align_up(bar_off + 64, 256);
-    const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;
-    int head = 1;
-    while ((1 << head) < iters / 2 + 2) ++head;
-    for (int c = 0; c < 2; ++c) {
-        TIMET_CUDA(cudaMemsetAsync(wsp[c] + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
-        SkResArgs &R = P.a[c];
-        R.chan = 0; R.g_first = 0; R.g_size = 0; R.ll = E.sk_ll;
-        R.ustride = ustride;
-        R.ufix_scale = ldexpf(1.0f, 47 - head);
-        R.ufix_inv = ldexpf(1.0f, head - 47);
-        R.ufix = (unsigned long long *)(wsp[c] + ufix_off);
-        R.out_block_rows = op[c] ? op[c]->out_block_rows : 0;
-        R.out_block_stride = op[c] ? op[c]->out_block_stride : 0;
-        R.in = in[c]; R.q_out = qo[c]; R.partials = (float *)wsp[c]; R.bar = (unsigned int *)(wsp[0] + bar_off);
-        R.B = B; R.K = K; R.iters = iters; R.rows_per_cta = rpc; R.scores_mode = (input_kind == TIMET_SK_SCORES);
-        R.inv_eps = (input_kind == TIMET_SK_SCORES) ? 1.0f / epsilon : 0.f;
-        R.r = 1.0f / (float)K; R.c = 1.0f / ((float)B * (float)world_size);
-        R.peers = p2p ? peers : nullptr; R.rank = prank; R.ws = p2p ? pws : 1;
-        R.epoch0 = p2p ? *pepoch : 0ull;
-        R.timeout_ns = (unsigned long long)(E.p2p_timeout_s * 1e9);
-    }
-    if (p2p) *pepoch += 2ull * (unsigned long long)iters;      // per problem: pass 0 + (iters - 1) iterations
-    switch ((K / 4 + 31) / 32) {
-        case 1: return sk_pair_launch<1>(P, rgrid, rsmem, st);
-        case 2: return sk_pair_launch<2>(P, rgrid, rsmem, st);
-        default: return sk_pair_launch<3>(P, rgrid, rsmem, st);
-    }
+    // not a dual launch: two independent calls (each validates its own arguments)
+    int rc = timet_sinkhorn_ex(in0, B, K, input_kind, epsilon, iters, world_size, comm, q0, opts0, wsp[0], one, stream);
+    if (rc != TIMET_OK) return rc;
+    return timet_sinkhorn_ex(in1, B, K, input_kind, epsilon, iters, world_size, comm, q1, opts1, wsp[1], one, stream);
 }
 
 }

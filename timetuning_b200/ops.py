@@ -99,10 +99,10 @@ def sinkhorn_from_scores(scores: torch.Tensor, epsilon: float, nmb_iters: int, w
 
 @torch.no_grad()
 def sinkhorn_pair_from_scores(scores0, scores1, epsilon: float, nmb_iters: int, world_size: int = 1, out0=None, out1=None):
-    """Two find_optimal_assignment calls of the same shape in ONE resident launch (the source and target assignment of a
-    training step, time_tuning.py:268,275): the kernel sweeps one problem while the other waits for its grid-wide marginal
-    reduction.  Bit-identical to two sinkhorn_from_scores calls.  scores0/1 [B, K] CUDA float32 -> (Q0, Q1); out0 / out1
-    as in sinkhorn_from_scores."""
+    """Two find_optimal_assignment calls of the same shape in ONE launch (the source and target assignment of a training
+    step, time_tuning.py:268,275): the two problems run side by side on half of the SMs each, so their latency-bound
+    reduction chains overlap.  Equal to two sinkhorn_from_scores calls within fp32 summation order, bit-reproducible.
+    scores0/1 [B, K] CUDA float32 -> (Q0, Q1); out0 / out1 as in sinkhorn_from_scores."""
     S = [_to_cuda(x.detach()).float().contiguous() for x in (scores0, scores1)]
     if S[0].dim() != 2 or S[0].shape != S[1].shape:
         raise ValueError(f"two score matrices of the same shape [B, K] expected, got {tuple(S[0].shape)} and {tuple(S[1].shape)}")
@@ -141,8 +141,8 @@ def sinkhorn_mode(B: int, K: int) -> str:
 
 
 def sinkhorn_pair_mode(B: int, K: int) -> str:
-    """How sinkhorn_pair_from_scores runs: "dual" (one launch, the two problems side by side), "interleaved" or "sequential"."""
-    return ("sequential", "dual", "interleaved")[int(_cabi.lib().timet_sinkhorn_pair_mode(int(B), int(K)))]
+    """How sinkhorn_pair_from_scores runs: "dual" (one launch, the two problems side by side) or "sequential"."""
+    return ("sequential", "dual")[int(_cabi.lib().timet_sinkhorn_pair_mode(int(B), int(K)))]
 
 
 def sinkhorn_is_resident(B: int, K: int) -> bool:
