@@ -6,8 +6,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-VARIANTS = [{}, {"TIMET_FIN_BATCH": "4"}, {"TIMET_FIN_BATCH": "6"}, {"TIMET_FIN_BATCH": "8"},
-            {"TIMET_GATHER_BATCH": "4"}, {"TIMET_GATHER_BATCH": "5"}, {"TIMET_GATHER_BATCH": "7"}]
+VARIANTS = [{}, {"TIMET_GATHER_BATCH": "5"}, {"TIMET_GATHER_BATCH": "7"}, {"TIMET_SK_DUAL": "0"}, {"TIMET_SC_STAGES": "4"},
+            {"TIMET_SK_STREAMING": "1"}]
 extra = sys.argv[1:]
 for env in VARIANTS:
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-e2e",

@@ -50,7 +50,6 @@ void env_reload() {
     e.sk_no_dual = env_int("TIMET_SK_DUAL", 1) == 0;     // 0: the two calls of timet_sinkhorn_pair one after the other
     e.sk_ll = env_int("TIMET_SK_LL", 1) != 0 ? 1 : 0;
     e.sk_ustride = env_int("TIMET_SK_USTRIDE", 0);
-    e.fin_batch = env_int("TIMET_FIN_BATCH", 0);
     e.gather_batch = env_int("TIMET_GATHER_BATCH", 0);
     e.sc_stages = env_int("TIMET_SC_STAGES", 0);
     const char *to = getenv("TIMET_P2P_TIMEOUT_S");
