@@ -333,13 +333,15 @@ __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[N
 // the world_size vectors in rank order (bit-identical on all ranks).  `vec` (shared memory, [K]) holds the local
 // vector on entry and the global sum on exit.  A slot is reused after 3 exchanges; a peer can only be one exchange
 // ahead, so it is never overwritten while still being read.
-// Low-latency exchange (default): every value is sent as ONE 8-byte word (float bits | tag = exchange number + 1 in the
-// high half).  The leader CTA of the problem stores the rank's K words into every rank's buffer; every CTA of every rank
+// Low-latency exchange (default): every value is sent as ONE 8-byte word (float bits | tag = exchange number in the high
+// half).  The leader CTA of the problem stores the rank's K words into every rank's buffer; every CTA of every rank
 // polls the K x world_size words of its own buffer until their tags match and adds the values in rank order.  An 8-byte
 // store is single-copy atomic, so data and "flag" arrive together: no fence, no second round trip.  (32-bit non-zero
 // tags; a slot is reused every 3 exchanges, so a stale word can never carry the awaited tag.)
+// The words of a column are polled four ranks at a time (independent loads: one L2 round trip per four ranks, not one per
+// rank); arrived values are parked in `scratch` ([world_size, K] floats of shared memory) and summed in rank order.
 template <int SKR_THREADS>
-__device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned long long e, float *vec) {
+__device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned long long e, float *vec, float *scratch) {
     const int K = A.K;
     P2PBuf *own = reinterpret_cast<P2PBuf *>(A.peers[A.rank]) + A.chan;
     const int slot = (int)(e % 3ull);
@@ -354,27 +356,35 @@ __device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned lon
     }
     __syncthreads();                                   // vec is rewritten below
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
-        float t = 0.f;
-        for (int r = 0; r < A.ws; ++r) {
-            const unsigned long long *src = &own->ll[slot][r][i];
-            unsigned long long v, t0 = 0ull;
+        for (int r0 = 0; r0 < A.ws; r0 += 4) {
+            unsigned pending = (A.ws - r0 >= 4) ? 0xFu : ((1u << (A.ws - r0)) - 1u);
+            unsigned long long t0 = 0ull;
             unsigned int spins = 0;
-            do {
-                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
-                if ((v & 0xFFFFFFFF00000000ull) == tag) break;
-                if ((++spins & 0xFFFu) == 0u) {
+            while (pending) {
+                unsigned long long v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (pending & (1u << u)) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v[u]) : "l"(&own->ll[slot][r0 + u][i]) : "memory");
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if ((pending & (1u << u)) && (v[u] & 0xFFFFFFFF00000000ull) == tag) {
+                        scratch[(r0 + u) * K + i] = __uint_as_float((unsigned int)(v[u] & 0xFFFFFFFFull));
+                        pending &= ~(1u << u);
+                    }
+                if (pending && (++spins & 0x3FFu) == 0u) {
                     const unsigned long long now = globaltimer_ns();
                     if (t0 == 0ull) t0 = now;
                     else if (now - t0 > A.timeout_ns) {
-                        printf("timet: sinkhorn peer exchange timed out after %llu s (rank %d waiting for rank %d, exchange %llu)\n",
-                               A.timeout_ns / 1000000000ull, A.rank, r, e);
+                        printf("timet: sinkhorn peer exchange timed out after %llu s (rank %d still waiting for ranks %d + mask 0x%x, exchange %llu)\n",
+                               A.timeout_ns / 1000000000ull, A.rank, r0, pending, e);
                         __trap();
                     }
                     __nanosleep(100);
                 }
-            } while (true);
-            t += __uint_as_float((unsigned int)(v & 0xFFFFFFFFull));
+            }
         }
+        float t = 0.f;
+        for (int r = 0; r < A.ws; ++r) t += scratch[r * K + i];     // rank order: identical bits on every rank (own writes, own reads)
         vec[i] = t;
     }
     __syncthreads();
@@ -426,9 +436,10 @@ __device__ __forceinline__ void skr_exchange_flag(const SkResArgs &A, unsigned l
     __syncthreads();
 }
 
+// `scratch`: [world_size, K] floats of shared memory that do not overlap `vec` (the low-latency form parks arrivals there)
 template <int SKR_THREADS>
-__device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long long e, float *vec) {
-    if (A.ll) skr_exchange_ll<SKR_THREADS>(A, e, vec);
+__device__ __forceinline__ void skr_exchange(const SkResArgs &A, unsigned long long e, float *vec, float *scratch) {
+    if (A.ll) skr_exchange_ll<SKR_THREADS>(A, e, vec, scratch);
     else skr_exchange_flag<SKR_THREADS>(A, e, vec);
 }
 
@@ -567,7 +578,7 @@ __global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_re
     grid_barrier(A.bar, (++epoch) * gridDim.x);
     fold_partials<SKR_THREADS>(A.partials, gridDim.x, K, red, a_s, 0.f);      // a_s = local column sums
     unsigned long long xch = A.epoch0;
-    if (A.ws > 1) skr_exchange<SKR_THREADS>(A, xch++, a_s);
+    if (A.ws > 1) skr_exchange<SKR_THREADS>(A, xch++, a_s, red);
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) a_s[i] = __fdiv_rn(A.r, a_s[i]);
     __syncthreads();
 
@@ -614,7 +625,7 @@ __global__ void __launch_bounds__(SKR_THREADS, SKR_THREADS == 512 ? 2 : 1) sk_re
         __syncthreads();                                               // everyone is done with the fold scratch
         if (i < K) red[i] = u_mine;
         __syncthreads();
-        if (A.ws > 1) skr_exchange<SKR_THREADS>(A, xch++, red);                     // u_i summed over ranks (my_utils.py:270-272)
+        if (A.ws > 1) skr_exchange<SKR_THREADS>(A, xch++, red, red + K);                     // u_i summed over ranks (my_utils.py:270-272)
         if (i < K) a_s[i] = a_s[i] * __fdiv_rn(A.r, red[i]);           // Q *= r / u  (my_utils.py:268)
         __syncthreads();
     }
@@ -645,7 +656,7 @@ __device__ __forceinline__ void skp_post(const SkResArgs &A, int it, float *red,
 // and apply Q *= r / u to the scaling vector (my_utils.py:268)
 template <int THREADS>
 __device__ __forceinline__ void skp_wait(const SkResArgs &A, int it, unsigned long long &prev0, unsigned long long &prev1,
-                                         unsigned long long &xch, float *a_s, float *u_s) {
+                                         unsigned long long &xch, float *a_s, float *u_s, float *red) {
     const int K = A.K;
     const int i = threadIdx.x;
     if (i < K) {
@@ -671,7 +682,7 @@ __device__ __forceinline__ void skp_wait(const SkResArgs &A, int it, unsigned lo
         if (it & 1) prev1 = cur; else prev0 = cur;
     }
     __syncthreads();
-    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, u_s);
+    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, u_s, red);
     if (i < K) a_s[i] = a_s[i] * __fdiv_rn(A.r, u_s[i]);
     __syncthreads();
 }
@@ -732,7 +743,7 @@ __global__ void __launch_bounds__(1024, 1) sk_hybrid(SkPairArgs P, int nprob, in
     grid_barrier(A.bar, (unsigned)G);                   // the CTAs of this problem only (own counter)
     fold_partials<THREADS>(A.partials, (unsigned)G, K, red, a_s, 0.f);
     unsigned long long xch = A.epoch0;
-    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_s);
+    if (A.ws > 1) skr_exchange<THREADS>(A, xch++, a_s, red);
     for (int i = threadIdx.x; i < K; i += THREADS) a_s[i] = __fdiv_rn(A.r, a_s[i]);
     __syncthreads();
 
@@ -743,7 +754,7 @@ __global__ void __launch_bounds__(1024, 1) sk_hybrid(SkPairArgs P, int nprob, in
         skp_sweep<NV4, WARPS, false, false>(A, nullptr, row0 + nres, nrows - nres, a_s, acc, last, warp, lane);
         if (last) break;
         skp_post<NV4, WARPS>(A, it, red, acc, warp, lane);
-        skp_wait<THREADS>(A, it, p0, p1, xch, a_s, u_s);
+        skp_wait<THREADS>(A, it, p0, p1, xch, a_s, u_s, red);
     }
 }
 
@@ -907,7 +918,7 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
             const int ustride = (E.sk_ustride >= 1 && E.sk_ustride <= SKR_USTRIDE) ? E.sk_ustride : SKR_USTRIDE;   // 1 = packed accumulators (for comparison)
             TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
             SkResArgs R;
-            R.chan = 0; R.g_first = 0; R.g_size = 0; R.ll = E.sk_ll;
+            R.chan = 0; R.g_first = 0; R.g_size = 0; R.ll = (E.sk_ll && world_size <= 15) ? 1 : 0;
             R.ustride = ustride;
             // 48 data bits: the marginals of one iteration sum to <= 1 and a buffer accumulates ceil(iters / 2) of them
             int head = 1;
@@ -944,7 +955,7 @@ int timet_sinkhorn_ex(const float *in, int64_t B, int K, int input_kind, float e
             TIMET_CUDA(cudaMemsetAsync((char *)workspace + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
             SkPairArgs HP;
             SkResArgs &R = HP.a[0];
-            R.chan = 0; R.g_first = 0; R.g_size = hgrid; R.ll = E.sk_ll;
+            R.chan = 0; R.g_first = 0; R.g_size = hgrid; R.ll = (E.sk_ll && world_size <= 15) ? 1 : 0;
             R.ustride = ustride;
             int head = 1;
             while ((1 << head) < iters / 2 + 2) ++head;
@@ -1052,7 +1063,7 @@ int timet_sinkhorn_pair(const float *in0, const float *in1, int64_t B, int K, in
             for (int c = 0; c < 2; ++c) {
                 TIMET_CUDA(cudaMemsetAsync(wsp[c] + bar_off, 0, ufix_off - bar_off + 2 * (size_t)K * ustride * sizeof(unsigned long long), st));
                 SkResArgs &R = P.a[c];
-                R.chan = c; R.g_first = c * dgrid; R.g_size = dgrid; R.ll = E.sk_ll;
+                R.chan = c; R.g_first = c * dgrid; R.g_size = dgrid; R.ll = (E.sk_ll && world_size <= 15) ? 1 : 0;
                 R.ustride = ustride;
                 R.ufix_scale = ldexpf(1.0f, 47 - head);
                 R.ufix_inv = ldexpf(1.0f, head - 47);
