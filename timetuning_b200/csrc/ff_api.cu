@@ -72,8 +72,8 @@ int timet_ff_select(const timet_ff_params *p, int engine, const float *feats, vo
     TIMET_CHECK_ARG(engine == TIMET_FF_EXACT || engine == TIMET_FF_TC || engine == TIMET_FF_AUTO, "ff_select: bad engine %d", engine);
     cudaStream_t st = (cudaStream_t)stream;
     char *ws = (char *)workspace;
-    TIMET_CUDA(cudaMemsetAsync(ws + L.off_stats, 0, 8 * sizeof(int64_t) + 0, st));
-    TIMET_CUDA(cudaMemsetAsync(ws + L.off_redo, 0, 256, st));
+    // diagnostics counters + the header of the re-do region (re-do count, work counter, wide-pool fill) are adjacent: one memset
+    TIMET_CUDA(cudaMemsetAsync(ws + L.off_stats, 0, (L.off_redo - L.off_stats) + 256, st));
     if (engine == TIMET_FF_AUTO) engine = ff_tc_supported(*p) ? TIMET_FF_TC : TIMET_FF_EXACT;
     if (engine == TIMET_FF_TC) {
         if (!ff_tc_supported(*p)) {

@@ -95,6 +95,7 @@ ff_select_exact_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw,
     const int H = p.grid_h, W = p.grid_w;
     const int64_t total = qlist ? (int64_t)*qcount : n_queries;
     const int64_t nwarps = (int64_t)gridDim.x * EX_WARPS;
+    if (qlist && blockIdx.x == 0 && threadIdx.x == 0) stats[4] = (unsigned long long)*qcount;   // queries re-done after a candidate-list overflow
     unsigned long long st_sel = 0, st_ties = 0, st_trunc = 0, st_wide = 0;
 
     for (int64_t it = (int64_t)blockIdx.x * EX_WARPS + warp; it < total; it += nwarps) {

@@ -467,10 +467,6 @@ ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw, uint32_t w
     }
 }
 
-__global__ void ff_redo_count_kernel(const unsigned int *redo_count, unsigned long long *stats) {
-    stats[4] = *redo_count;
-}
-
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -635,8 +631,6 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float
     TIMET_LAUNCHED();
     // overflowed queries: exact scan (device-side count; a fixed small grid loops over the list)
     if ((rc = ff_select_exact_run(p, L, feats, ws, redo_list, redo_count, (int64_t)num_sms() * 8 * 8, st)) != TIMET_OK) return rc;
-    ff_redo_count_kernel<<<1, 1, 0, st>>>(redo_count, reinterpret_cast<unsigned long long *>(ws + L.off_stats));
-    TIMET_LAUNCHED();
     return TIMET_OK;
 }
 

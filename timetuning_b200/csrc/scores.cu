@@ -33,53 +33,67 @@ __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) 
     return pk;
 }
 
-// One warp per row: x^ = x / max(||x||, 1e-12) (normalize = 1) or x itself -> [hi | lo] fp16, 2 * dhp wide.
-// dh % 4 == 0: 128-bit loads, the lane's slice kept in registers (dh <= 512), 64-bit stores of 4 halfs.
+// One warp per row: x^ = x / max(||x||, 1e-12) (normalize) or x itself -> [hi | lo] fp16, 2 * dhp wide; src == nullptr
+// writes a zero row.  dh % 4 == 0: 128-bit loads, the lane's slice kept in registers (dh <= 512), 64-bit stores of 4 halfs.
+__device__ __forceinline__ void scores_prep_row(const float *__restrict__ src, __half *__restrict__ dst, int dh, int dhp,
+                                                bool normalize, int lane) {
+    constexpr int KEEP = 4;
+    if (src == nullptr) {
+        for (int i = lane; i < (dhp >> 1); i += 32) reinterpret_cast<uint2 *>(dst)[i] = make_uint2(0u, 0u);   // 2 * dhp halfs
+        return;
+    }
+    if ((dh & 3) == 0 && (dh >> 2) <= 32 * KEEP && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        float4 v[KEEP];
+        float ss = 0.f;
+#pragma unroll
+        for (int u = 0; u < KEEP; ++u) {
+            const int i = lane + 32 * u;
+            v[u] = (i < (dh >> 2)) ? __ldg(reinterpret_cast<const float4 *>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss = fmaf(v[u].x, v[u].x, ss); ss = fmaf(v[u].y, v[u].y, ss); ss = fmaf(v[u].z, v[u].z, ss); ss = fmaf(v[u].w, v[u].w, ss);
+        }
+        ss = warp_sum(ss);
+        const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+#pragma unroll
+        for (int u = 0; u < KEEP; ++u) {
+            const int i = lane + 32 * u;
+            if (i < (dhp >> 2)) {
+                const float a = __fdiv_rn(v[u].x, denom), b = __fdiv_rn(v[u].y, denom), c = __fdiv_rn(v[u].z, denom), d = __fdiv_rn(v[u].w, denom);
+                const uint2 hi = pack_half4(a, b, c, d);
+                const __half2 h01 = *reinterpret_cast<const __half2 *>(&hi.x), h23 = *reinterpret_cast<const __half2 *>(&hi.y);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                reinterpret_cast<uint2 *>(dst)[i] = hi;
+                reinterpret_cast<uint2 *>(dst + dhp)[i] = pack_half4(a - f01.x, b - f01.y, c - f23.x, d - f23.y);
+            }
+        }
+        return;
+    }
+    float ss = 0.f;
+    for (int i = lane; i < dh; i += 32) { const float v = src[i]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+    for (int i = lane; i < dhp; i += 32) {
+        const float v = (i < dh) ? __fdiv_rn(src[i], denom) : 0.f;
+        const __half hi = __float2half_rn(v);
+        dst[i] = hi;
+        dst[dhp + i] = __float2half_rn(v - __half2float(hi));
+    }
+}
+
+// ONE launch prepares both GEMM operands: logical rows [0, B) = feature rows (normalised) -> a2; [B, B + K) = the prototypes
+// as given (time_tuning.py:138,140) -> b2; [B + K, B + Kp) = zero padding of b2 up to the MMA's N tile.
 __global__ void __launch_bounds__(256)
-scores_prep_kernel(ScInputs in, __half *__restrict__ out, int64_t rows, int dh, int dhp, int normalize) {
+scores_prep_kernel(ScInputs in, const float *__restrict__ prototypes, __half *__restrict__ a2, __half *__restrict__ b2, int64_t B,
+                   int K, int Kp, int dh, int dhp) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    constexpr int KEEP = 4;
-    const bool vec = (dh & 3) == 0 && (dh >> 2) <= 32 * KEEP;
-    for (int64_t row = warp; row < rows; row += nwarps) {
-        const int64_t blk = row / in.rows_each;
-        const float *src = in.x[blk] + (row - blk * in.rows_each) * dh;
-        __half *dst = out + row * 2 * dhp;
-        if (vec && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            float4 v[KEEP];
-            float ss = 0.f;
-#pragma unroll
-            for (int u = 0; u < KEEP; ++u) {
-                const int i = lane + 32 * u;
-                v[u] = (i < (dh >> 2)) ? __ldg(reinterpret_cast<const float4 *>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                ss = fmaf(v[u].x, v[u].x, ss); ss = fmaf(v[u].y, v[u].y, ss); ss = fmaf(v[u].z, v[u].z, ss); ss = fmaf(v[u].w, v[u].w, ss);
-            }
-            ss = warp_sum(ss);
-            const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-#pragma unroll
-            for (int u = 0; u < KEEP; ++u) {
-                const int i = lane + 32 * u;
-                if (i < (dhp >> 2)) {
-                    const float a = __fdiv_rn(v[u].x, denom), b = __fdiv_rn(v[u].y, denom), c = __fdiv_rn(v[u].z, denom), d = __fdiv_rn(v[u].w, denom);
-                    const uint2 hi = pack_half4(a, b, c, d);
-                    const __half2 h01 = *reinterpret_cast<const __half2 *>(&hi.x), h23 = *reinterpret_cast<const __half2 *>(&hi.y);
-                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                    reinterpret_cast<uint2 *>(dst)[i] = hi;
-                    reinterpret_cast<uint2 *>(dst + dhp)[i] = pack_half4(a - f01.x, b - f01.y, c - f23.x, d - f23.y);
-                }
-            }
-            continue;
-        }
-        float ss = 0.f;
-        for (int i = lane; i < dh; i += 32) { const float v = src[i]; ss = fmaf(v, v, ss); }
-        ss = warp_sum(ss);
-        const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-        for (int i = lane; i < dhp; i += 32) {
-            const float v = (i < dh) ? __fdiv_rn(src[i], denom) : 0.f;
-            const __half hi = __float2half_rn(v);
-            dst[i] = hi;
-            dst[dhp + i] = __float2half_rn(v - __half2float(hi));
+    for (int64_t row = warp; row < B + Kp; row += nwarps) {
+        if (row < B) {
+            const int64_t blk = row / in.rows_each;
+            scores_prep_row(in.x[blk] + (row - blk * in.rows_each) * dh, a2 + row * 2 * dhp, dh, dhp, true, lane);
+        } else {
+            const int64_t k = row - B;
+            scores_prep_row(k < K ? prototypes + k * dh : nullptr, b2 + k * 2 * dhp, dh, dhp, false, lane);
         }
     }
 }
@@ -225,17 +239,10 @@ int timet_cosine_scores_multi(const float *const *x_list, int n_x, int64_t rows_
     const int64_t Kp = (K + 255) / 256 * 256;
     __half *a2 = reinterpret_cast<__half *>(workspace);
     __half *b2 = reinterpret_cast<__half *>((char *)workspace + align_up((size_t)(B + 128) * 2 * dhp * sizeof(__half), 1024));
-    TIMET_CUDA(cudaMemsetAsync(b2, 0, (size_t)Kp * 2 * dhp * sizeof(__half), st));      // padded prototype rows = 0
-    int64_t pb = (B + 7) / 8;
+    int64_t pb = (B + Kp + 7) / 8;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (pb > cap) pb = cap;
-    scores_prep_kernel<<<(int)pb, 256, 0, st>>>(in, a2, B, dh, dhp, 1);
-    TIMET_LAUNCHED();
-    ScInputs pin;
-    pin.rows_each = K;
-    pin.x[0] = prototypes;
-    for (int i = 1; i < SC_MAX_INPUTS; ++i) pin.x[i] = nullptr;
-    scores_prep_kernel<<<(K + 7) / 8, 256, 0, st>>>(pin, b2, K, dh, dhp, 0);      // prototypes are used as given (:138,:140)
+    scores_prep_kernel<<<(int)pb, 256, 0, st>>>(in, prototypes, a2, b2, B, K, (int)Kp, dh, dhp);
     TIMET_LAUNCHED();
 
     const int n_tiles = (int)((K + 255) / 256);
