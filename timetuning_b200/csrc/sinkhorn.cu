@@ -338,8 +338,9 @@ __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[N
 // polls the K x world_size words of its own buffer until their tags match and adds the values in rank order.  An 8-byte
 // store is single-copy atomic, so data and "flag" arrive together: no fence, no second round trip.  (32-bit non-zero
 // tags; a slot is reused every 3 exchanges, so a stale word can never carry the awaited tag.)
-// The words of a column are polled four ranks at a time (independent loads: one L2 round trip per four ranks, not one per
-// rank); arrived values are parked in `scratch` ([world_size, K] floats of shared memory) and summed in rank order.
+// The words of a column are polled LL_CHUNK = 8 ranks at a time (independent loads: one L2 round trip for a whole 8-GPU
+// node, not one per rank); arrived values are parked in `scratch` ([world_size, K] floats of shared memory) and summed in rank order.
+constexpr int LL_CHUNK = 8;
 template <int SKR_THREADS>
 __device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned long long e, float *vec, float *scratch) {
     const int K = A.K;
@@ -356,17 +357,17 @@ __device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned lon
     }
     __syncthreads();                                   // vec is rewritten below
     for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
-        for (int r0 = 0; r0 < A.ws; r0 += 4) {
-            unsigned pending = (A.ws - r0 >= 4) ? 0xFu : ((1u << (A.ws - r0)) - 1u);
+        for (int r0 = 0; r0 < A.ws; r0 += LL_CHUNK) {
+            unsigned pending = (A.ws - r0 >= LL_CHUNK) ? ((1u << LL_CHUNK) - 1u) : ((1u << (A.ws - r0)) - 1u);
             unsigned long long t0 = 0ull;
             unsigned int spins = 0;
             while (pending) {
-                unsigned long long v[4];
+                unsigned long long v[LL_CHUNK];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < LL_CHUNK; ++u)
                     if (pending & (1u << u)) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v[u]) : "l"(&own->ll[slot][r0 + u][i]) : "memory");
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < LL_CHUNK; ++u)
                     if ((pending & (1u << u)) && (v[u] & 0xFFFFFFFF00000000ull) == tag) {
                         scratch[(r0 + u) * K + i] = __uint_as_float((unsigned int)(v[u] & 0xFFFFFFFFull));
                         pending &= ~(1u << u);
