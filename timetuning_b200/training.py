@@ -123,39 +123,45 @@ def fast_get_loss(self, x, annotations=None, n_last_frames=7, size_mask_neighbor
                   sinkhorn_iterations=10, mask_features=False, return_aux=False):
     """Drop-in for TimeT.get_loss (time_tuning.py:224-302), same arguments and defaults, same loss value.
 
-    Feature extraction, attention masking and the queue update are the reference's own statements (:231-261, same RNG
-    consumption); everything from :263 on is the batched path described in the module docstring."""
-    bs, fs, c, h, w = x.shape
+    Feature extraction, attention masking and the queue update make the same calls in the same order as :231-261 (same RNG
+    consumption, same queue content); everything from :263 on is the batched path described in the module docstring."""
+    bs, fs = x.shape[:2]
+    frames = x.flatten(0, 1)                                                          # [bs * fs, c, h, w]
     fe = self.feature_extractor
     sr = fe.spatial_resolution
     mod = _ref_module(self)
-    teacher_features = None
-    if self.teacher is not None:                                                      # :231-236
-        teacher_features, teacher_attentions = self.teacher(x.view(bs * fs, c, h, w))
-        _, num_patches, dim = teacher_features.shape
-        teacher_features = teacher_features.view(bs, fs, num_patches, dim)
+    has_teacher = self.teacher is not None
+
+    def per_clip(t):                                                                  # [bs * fs, N, d] -> [bs, fs, N, d]
+        return t.view(bs, fs, t.shape[-2], t.shape[-1])
+
+    # ---- feature extraction, same calls in the same order as :231-246 (teacher, student head, student backbone)
+    teacher_feats = None
+    if has_teacher:
+        t_out, t_attn = self.teacher(frames)
+        teacher_feats = per_clip(t_out)
         if mask_features:
-            teacher_features, teacher_attentions = mod.apply_attention_mask(teacher_features, teacher_attentions, sr)
-    features, attentions = fe(x.view(bs * fs, c, h, w))                               # :237
+            teacher_feats, t_attn = mod.apply_attention_mask(teacher_feats, t_attn, sr)
+    head_out, attentions = fe(frames)
     with torch.no_grad():
-        backbone_features, _ = fe(x.view(bs * fs, c, h, w), use_head=False)           # :238-239
-    _, num_patches, dim = features.shape
-    features = features.view(bs, fs, num_patches, dim)
-    backbone_features = backbone_features.view(bs, fs, num_patches, backbone_features.shape[-1])
-    if mask_features:                                                                 # :244-246
+        backbone_out, _ = fe(frames, use_head=False)
+    features, backbone_features = per_clip(head_out), per_clip(backbone_out)
+    num_patches, dim = features.shape[-2:]
+    if mask_features:
         features, attentions = mod.apply_attention_mask(features, attentions, sr)
         attentions = attentions.view(bs, fs, sr, sr)
 
-    if self.queue is not None:                                                        # :250-261 (unchanged)
-        queue_features = (teacher_features if self.teacher is not None else features)[:, 0].reshape(-1, dim)
-        num_vectors_to_store = min(bs * 10, self.queue.size(0))
-        idx = torch.randperm(queue_features.size(0))[:num_vectors_to_store]
-        self.queue[num_vectors_to_store:] = self.queue[:-num_vectors_to_store].clone()
-        self.queue[:num_vectors_to_store] = queue_features[idx].detach()
+    # ---- feature queue (:250-261): push a random subset of the source-frame vectors at the front, oldest fall off the end.
+    # One randperm of the same length as the reference draws, so the RNG stream and the queue content are identical.
+    if self.queue is not None:
+        src_vectors = (teacher_feats if has_teacher else features)[:, 0].reshape(-1, dim).detach()
+        n_new = min(10 * bs, self.queue.size(0))
+        pick = torch.randperm(src_vectors.size(0))[:n_new]
+        self.queue.copy_(torch.cat([src_vectors[pick], self.queue[:self.queue.size(0) - n_new]], dim=0))
 
     # ---- assignment of the source frame (:263-268): the only Sinkhorn result the loss consumes
-    if self.teacher is not None:
-        batch_q = assignment(self, teacher_features[:, 0], epsilon, sinkhorn_iterations, use_teacher=True)
+    if has_teacher:
+        batch_q = assignment(self, teacher_feats[:, 0], epsilon, sinkhorn_iterations, use_teacher=True)
     else:
         batch_q = assignment(self, features[:, 0], epsilon, sinkhorn_iterations)
     # ---- student scores of the target frame (:269-275): the only scores the loss consumes; autograd stays in torch
