@@ -334,13 +334,12 @@ __device__ __forceinline__ void skr_fold_warps(float *red, const float4 (&acc)[N
 // vector on entry and the global sum on exit.  A slot is reused after 3 exchanges; a peer can only be one exchange
 // ahead, so it is never overwritten while still being read.
 // Low-latency exchange (default): every value is sent as ONE 8-byte word (float bits | tag = exchange number in the high
-// half).  The leader CTA of the problem stores the rank's K words into every rank's buffer; every CTA of every rank
-// polls the K x world_size words of its own buffer until their tags match and adds the values in rank order.  An 8-byte
-// store is single-copy atomic, so data and "flag" arrive together: no fence, no second round trip.  (32-bit non-zero
-// tags; a slot is reused every 3 exchanges, so a stale word can never carry the awaited tag.)
-// The words of a column are polled LL_CHUNK = 8 ranks at a time (independent loads: one L2 round trip for a whole 8-GPU
-// node, not one per rank); arrived values are parked in `scratch` ([world_size, K] floats of shared memory) and summed in rank order.
-constexpr int LL_CHUNK = 8;
+// half).  The leader CTA of the problem stores the rank's K words into every rank's buffer.  An 8-byte store is
+// single-copy atomic, so data and "flag" arrive together: no fence, no second round trip.  (32-bit non-zero tags; a slot
+// is reused every 3 exchanges, so a stale word can never carry the awaited tag.)
+// Receive: every CTA of every rank polls the K x world_size words of its own buffer, ONE WORD PER THREAD (all of them in
+// flight together: one L2 round trip for a whole node instead of one per rank, and no registers held across the sweep);
+// arrivals are parked in `scratch` ([world_size, K] floats of shared memory) and summed per column in rank order.
 template <int SKR_THREADS>
 __device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned long long e, float *vec, float *scratch) {
     const int K = A.K;
@@ -355,37 +354,31 @@ __device__ __forceinline__ void skr_exchange_ll(const SkResArgs &A, unsigned lon
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
         }
     }
-    __syncthreads();                                   // vec is rewritten below
-    for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
-        for (int r0 = 0; r0 < A.ws; r0 += LL_CHUNK) {
-            unsigned pending = (A.ws - r0 >= LL_CHUNK) ? ((1u << LL_CHUNK) - 1u) : ((1u << (A.ws - r0)) - 1u);
-            unsigned long long t0 = 0ull;
-            unsigned int spins = 0;
-            while (pending) {
-                unsigned long long v[LL_CHUNK];
-#pragma unroll
-                for (int u = 0; u < LL_CHUNK; ++u)
-                    if (pending & (1u << u)) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v[u]) : "l"(&own->ll[slot][r0 + u][i]) : "memory");
-#pragma unroll
-                for (int u = 0; u < LL_CHUNK; ++u)
-                    if ((pending & (1u << u)) && (v[u] & 0xFFFFFFFF00000000ull) == tag) {
-                        scratch[(r0 + u) * K + i] = __uint_as_float((unsigned int)(v[u] & 0xFFFFFFFFull));
-                        pending &= ~(1u << u);
-                    }
-                if (pending && (++spins & 0x3FFu) == 0u) {
-                    const unsigned long long now = globaltimer_ns();
-                    if (t0 == 0ull) t0 = now;
-                    else if (now - t0 > A.timeout_ns) {
-                        printf("timet: sinkhorn peer exchange timed out after %llu s (rank %d still waiting for ranks %d + mask 0x%x, exchange %llu)\n",
-                               A.timeout_ns / 1000000000ull, A.rank, r0, pending, e);
-                        __trap();
-                    }
-                    __nanosleep(100);
+    for (int idx = threadIdx.x; idx < K * A.ws; idx += SKR_THREADS) {
+        const int r = idx / K, i = idx - r * K;
+        const unsigned long long *src = &own->ll[slot][r][i];
+        unsigned long long v, t0 = 0ull;
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if ((v & 0xFFFFFFFF00000000ull) == tag) break;
+            if ((++spins & 0x3FFu) == 0u) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0ull) t0 = now;
+                else if (now - t0 > A.timeout_ns) {
+                    printf("timet: sinkhorn peer exchange timed out after %llu s (rank %d waiting for rank %d, exchange %llu)\n",
+                           A.timeout_ns / 1000000000ull, A.rank, r, e);
+                    __trap();
                 }
+                __nanosleep(100);
             }
-        }
+        } while (true);
+        scratch[idx] = __uint_as_float((unsigned int)(v & 0xFFFFFFFFull));      // scratch[r * K + i]
+    }
+    __syncthreads();                                   // all arrivals parked; vec is rewritten below
+    for (int i = threadIdx.x; i < K; i += SKR_THREADS) {
         float t = 0.f;
-        for (int r = 0; r < A.ws; ++r) t += scratch[r * K + i];     // rank order: identical bits on every rank (own writes, own reads)
+        for (int r = 0; r < A.ws; ++r) t += scratch[r * K + i];     // rank order: identical bits on every rank
         vec[i] = t;
     }
     __syncthreads();
