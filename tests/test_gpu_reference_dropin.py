@@ -169,3 +169,57 @@ def test_sinkhorn_through_my_utils(ref, golden):
         assert mu.sinkhorn is tb.sinkhorn
     assert_close(q_new.cpu().numpy(), q_ref.cpu().numpy(), what="sinkhorn")
     assert_close(q_ref.cpu().numpy(), g["q"], what="reference on GPU vs its CPU fixture")
+
+
+class _TinyFE(torch.nn.Module):
+    """A small extractor with the structure of the reference's models.FeatureExtractor (models.py:903-1078): a backbone
+    reached through get_features(), an MLP head, forward(x, use_head) = get_features then head."""
+
+    def __init__(self, sr, dim=48, out=32):
+        super().__init__()
+        self.spatial_resolution, self.feature_dim = sr, out
+        self.patch = torch.nn.Conv2d(3, dim, kernel_size=4, stride=4)
+        self.mix = torch.nn.Linear(dim, dim)
+        self.head = torch.nn.Sequential(torch.nn.Linear(dim, 64), torch.nn.GELU(), torch.nn.Linear(64, out))
+        self.calls = 0
+
+    def get_features(self, x):
+        self.calls += 1
+        t = self.patch(x).flatten(2).permute(0, 2, 1)
+        return t + torch.tanh(self.mix(t)), None
+
+    def forward(self, x, use_head=True):
+        t, a = self.get_features(x)
+        if use_head:
+            n, p, d = t.shape
+            t = self.head(t.reshape(n * p, d)).view(n, p, -1)
+        return t, a
+
+
+def test_fast_get_loss_shares_one_backbone_forward(ref):
+    """the reference runs the student backbone twice per step (time_tuning.py:237-239); the fast path
+    runs it once when the extractor has the reference's structure -- same loss, same gradients (head AND backbone)."""
+    mu, mp, tt, _ = ref
+    sr, bs, fs, K = 8, 3, 4, 24
+
+    def run(fast):
+        torch.manual_seed(3)
+        fe = _TinyFE(sr).cuda()
+        model = tt.TimeT(fe, K).cuda()
+        tt.world_size = 1
+        mp.mask_neighborhood = None
+        x = torch.randn(bs, fs, 3, 4 * sr, 4 * sr, device="cuda")
+        if fast:
+            with tb.install(tt, mp, mu, fast_get_loss=True):
+                loss = model.get_loss(x, size_mask_neighborhood=3, topk=3)
+        else:
+            loss = model.get_loss(x, size_mask_neighborhood=3, topk=3)
+        loss.backward()
+        return loss.item(), fe.calls, fe.patch.weight.grad.clone(), fe.head[0].weight.grad.clone(), model.prototypes.grad.clone()
+
+    l0, c0, gp0, gh0, gq0 = run(False)
+    l1, c1, gp1, gh1, gq1 = run(True)
+    assert c0 == 2 and c1 == 1, (c0, c1)
+    assert abs(l0 - l1) < 2e-5 * max(1.0, abs(l0)), (l0, l1)
+    for a, b, what in ((gp1, gp0, "backbone grad"), (gh1, gh0, "head grad"), (gq1, gq0, "prototype grad")):
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), atol=1e-6, rtol=1e-4, what=what)

@@ -210,11 +210,12 @@ static int ff_gather_launch_gb(const timet_ff_params &p, const FFLayout &L, floa
     return TIMET_OK;
 }
 
-// Gathered rows in flight per batch.  Measured at BASELINE configs[1] (topk 5): 4 -> 0.180 ms, 5 -> 0.220 ms (one round
-// trip per query but the two extra float4 per lane spill), 7 -> 0.332 ms; 4 is the default (env TIMET_GATHER_BATCH).
+// Gathered rows in flight per batch (env TIMET_GATHER_BATCH).  Measured at BASELINE configs[1] (topk 5) on the final kernel
+// (62 registers at 4): 4 -> 0.149 ms, 5 -> 0.141 ms (one round trip per query), 7 -> 0.146 ms; before the warp-uniform row
+// loop (spills) the order was reversed (0.180 / 0.220 / 0.332).  Default: 5 for the training top-k of 5, else 4.
 int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
                      cudaStream_t st) {
-    const int gb = env_cfg().gather_batch ? env_cfg().gather_batch : 4;
+    const int gb = env_cfg().gather_batch ? env_cfg().gather_batch : (p.topk == 5 ? 5 : 4);
     if (gb == 5) return ff_gather_launch_gb<5>(p, L, labels, hard, ws, st);
     if (gb >= 7) return ff_gather_launch_gb<7>(p, L, labels, hard, ws, st);
     return ff_gather_launch_gb<4>(p, L, labels, hard, ws, st);

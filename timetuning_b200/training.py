@@ -16,6 +16,9 @@ What ``fast_get_loss`` does differently from the reference, with an identical lo
     Feature-Forwarding call; the last-frame ``argmax`` is fused into it (hard labels int64 [bs, sr, sr]).
   * The cross entropy is evaluated for all clips at once (per-clip means averaged over the batch = the reference's
     ``batch_loss / bs``).
+  * ONE student backbone forward instead of two (``_extract``): the tokens feed the head with autograd
+    and, detached, the Feature-Forwarding, when the extractor has the reference's ``get_features`` / ``head`` structure and
+    no active dropout.
 PyTorch keeps what needs autograd (feature extractor, student scores, cross entropy).
 """
 from __future__ import annotations
@@ -118,9 +121,40 @@ def assignment(self, features, epsilon, sinkhorn_iterations, use_teacher=False):
     return q[:bs * num_patches].view(bs, num_patches, -1)
 
 
+# --------------------------------------------------------------------------- one backbone forward instead of two
+def _stochastic(module) -> bool:
+    """True if a forward pass of `module` draws random numbers (active Dropout / stochastic depth): two forward passes of
+    the reference then differ, and sharing one would change its statistics."""
+    for m in module.modules():
+        if m.training and ((isinstance(m, torch.nn.modules.dropout._DropoutNd) and m.p > 0) or float(getattr(m, "drop_prob", 0) or 0) > 0):
+            return True
+    return False
+
+
+def _extract(fe, frames, dedup):
+    """(head features, attentions, backbone features) of `frames`.
+
+    The reference calls the extractor twice per step (time_tuning.py:237-239): `fe(x)` and, under no_grad, `fe(x,
+    use_head=False)` -- two full backbone forwards whose token outputs are identical (models.py:1070-1078: forward =
+    get_features, then the head).  SURVEY.md §8f item 4: when the extractor exposes that structure (`get_features`, `head`)
+    and is deterministic, ONE backbone forward serves both: the tokens feed the head (with autograd) and, detached, the
+    Feature-Forwarding.  Anything else falls back to the reference's two calls."""
+    if dedup and callable(getattr(fe, "get_features", None)) and hasattr(fe, "head") and not _stochastic(fe):
+        tokens, attentions = fe.get_features(frames)
+        head_out = tokens
+        if fe.head is not None:
+            n, p, d = tokens.shape
+            head_out = fe.head(tokens.reshape(n * p, d)).view(n, p, -1)               # models.py:1072-1077
+        return head_out, attentions, tokens.detach()
+    head_out, attentions = fe(frames)
+    with torch.no_grad():
+        backbone_out, _ = fe(frames, use_head=False)
+    return head_out, attentions, backbone_out
+
+
 # --------------------------------------------------------------------------- TimeT.get_loss
 def fast_get_loss(self, x, annotations=None, n_last_frames=7, size_mask_neighborhood=6, topk=5, epsilon=0.05,
-                  sinkhorn_iterations=10, mask_features=False, return_aux=False):
+                  sinkhorn_iterations=10, mask_features=False, return_aux=False, dedup_backbone=True):
     """Drop-in for TimeT.get_loss (time_tuning.py:224-302), same arguments and defaults, same loss value.
 
     Feature extraction, attention masking and the queue update make the same calls in the same order as :231-261 (same RNG
@@ -135,16 +169,14 @@ def fast_get_loss(self, x, annotations=None, n_last_frames=7, size_mask_neighbor
     def per_clip(t):                                                                  # [bs * fs, N, d] -> [bs, fs, N, d]
         return t.view(bs, fs, t.shape[-2], t.shape[-1])
 
-    # ---- feature extraction, same calls in the same order as :231-246 (teacher, student head, student backbone)
+    # ---- feature extraction in the order of :231-246 (teacher, then student head + backbone features)
     teacher_feats = None
     if has_teacher:
         t_out, t_attn = self.teacher(frames)
         teacher_feats = per_clip(t_out)
         if mask_features:
             teacher_feats, t_attn = mod.apply_attention_mask(teacher_feats, t_attn, sr)
-    head_out, attentions = fe(frames)
-    with torch.no_grad():
-        backbone_out, _ = fe(frames, use_head=False)
+    head_out, attentions, backbone_out = _extract(fe, frames, dedup_backbone)          # one backbone forward where possible
     features, backbone_features = per_clip(head_out), per_clip(backbone_out)
     num_patches, dim = features.shape[-2:]
     if mask_features:
