@@ -136,6 +136,7 @@ def test_tc_random_features_worst_case():
     {"TIMET_TC_NBUF": "4"},                     # four 128-column TMEM buffers
     {"TIMET_TC_PFLAGS": "128"},                 # every TMEM buffer scanned by its own two groups
     {"TIMET_TC_PFLAGS": "72"},                  # oldest-first contexts, threshold picked up per tile
+    {"TIMET_TC_PFLAGS": "256"},                 # raster query tiles instead of column-blocked ones
 ], ids=lambda e: "+".join(f"{k[9:]}={v}" for k, v in e.items()))
 def test_tc_kernel_variants_are_bit_identical(timet_env, env):
     """Every kernel variant / schedule behind the experiment switches nominates a superset of the exact
@@ -153,6 +154,37 @@ def test_tc_kernel_variants_are_bit_identical(timet_env, env):
         w2, k2, n2 = plan.selection(c, t)
         assert torch.equal(n, n2) and torch.equal(k, k2) and torch.equal(w, w2), (env, c, t)
     assert st["redone_queries"] <= 0.02 * st["queries"], st
+
+
+@pytest.mark.parametrize("H,W,D,fs,radius,topk,bs", [
+    (28, 28, 384, 4, 1, 5, 2),       # narrow window: most TMEM columns are never read
+    (28, 28, 128, 4, 13, 7, 1),      # window wider than a column block's reach
+    (10, 30, 192, 4, 4, 4, 2),       # non-square, last tile has 2 of 4 grid rows
+    (7, 32, 64, 5, 15, 8, 2),        # full 32 columns (no padding lanes), radius at its maximum
+    (9, 26, 100, 4, 2, 3, 3),        # narrowest column-blocked grid, padded dim, last tile has 1 grid row
+    (5, 28, 384, 3, 6, 5, 1),        # two tiles per frame, the second with one grid row
+    (4, 30, 320, 9, 3, 5, 2),        # one tile per frame, FIFO eviction (n_last 3 below)
+])
+def test_tc_column_blocked_query_tiles(H, W, D, fs, radius, topk, bs):
+    """Grids 26..32 patches wide: the persistent kernel arranges a query tile as four 4 x 8 column blocks (one per TMEM
+    lane quadrant) and every epilogue warp reads only the key columns its block can see.  Same candidates => bit-identical
+    to the exact engine, for border / partial tiles and every chunk shape (16 / 8 / 4 TMEM columns)."""
+    N = H * W
+    rng = np.random.default_rng(H * 100 + W)
+    base = rng.standard_normal((bs, 1, N, D)).astype(np.float32)
+    feats = torch.from_numpy(base + 0.7 * rng.standard_normal((bs, fs, N, D)).astype(np.float32)).cuda()
+    n_last = 3 if fs > 8 else 7
+    plan = tb.FFPlan(bs, fs, H, W, D, 8, n_last, radius, topk)
+    assert plan.tc_supported
+    plan.prepare(feats)
+    plan.select(tb.FF_EXACT)
+    ref = {(c, t): [x.clone() for x in plan.selection(c, t)] for c in range(bs) for t in range(1, fs)}
+    plan.select(tb.FF_TC)
+    st = plan.stats()
+    for (c, t), (w, k, n) in ref.items():
+        w2, k2, n2 = plan.selection(c, t)
+        assert torch.equal(n, n2) and torch.equal(k, k2) and torch.equal(w, w2), (c, t)
+    assert st["redone_queries"] <= 0.05 * st["queries"], st
 
 
 def test_tc_engine_wide_features_dim_2048():

@@ -42,7 +42,7 @@ struct __align__(8) PsCtl {
 };
 
 struct Item {
-    int t, clip, qr0, nq, kr_lo, kr_hi, nchunks, nctx, ntiles, q_row0;
+    int t, clip, qr0, qr1, nq, kr_lo, kr_hi, nchunks, nctx, ntiles, q_row0;
     int64_t clip_row0;
 };
 
@@ -60,6 +60,7 @@ __device__ __forceinline__ Item item_geom(const TcGeom &G, int64_t id) {
     const int qt = rem % G.tiles_per_frame;
     I.qr0 = qt * G.QR;
     const int qr1 = min(G.H - 1, I.qr0 + G.QR - 1);
+    I.qr1 = qr1;
     I.nq = (qr1 - I.qr0 + 1) * G.W;
     I.kr_lo = max(0, I.qr0 - G.radius);
     I.kr_hi = min(G.H - 1, qr1 + G.radius);
@@ -151,7 +152,17 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 ptx::mbar_wait(&ctl->a_free, (k & 1u) ^ 1u);          // every MMA of the previous item has read A
                 if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
-                    for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, I.q_row0, &ctl->a_full);
+                    if (G.colblk) {
+                        // column-blocked query tile: quadrant w (tile rows 32w .. 32w+31 = the TMEM lanes of epilogue warps
+                        // 4g+w) holds the 4 x 8 block of queries (grid rows qr0 .. qr0+3, columns 8w .. 8w+7); one 3-D box
+                        // {64 elements, 8 patch columns, 4 grid rows} = 4 KB per quadrant and 64-wide K chunk
+                        const int grow0 = (I.clip * G.n_frames + I.t) * G.H + I.qr0;
+                        for (int kc = 0; kc < G.NKC; ++kc)
+                            for (int w = 0; w < 4; ++w)
+                                ptx::tma_load_3d(sA + kc * 16384 + w * 4096, &map_a, kc * 64, 8 * w, grow0, &ctl->a_full);
+                    } else {
+                        for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, I.q_row0, &ctl->a_full);
+                    }
                 }
             }
             for (int ci = 0; ci < I.nctx; ++ci) {
@@ -247,11 +258,18 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             if (id < 0) break;
             const Item I = item_geom(G, id);
             uint32_t *thr_cur = ctl->thr_sh[k & 1u];
-            const bool valid = qi < I.nq;
-            const int qrow = I.qr0 + qi / G.W, qcol = qi % G.W;
+            // query of this thread (= TMEM lane qi): raster order inside the tile, or -- column-blocked tile -- position
+            // (lane / 8, 8 * quadrant + lane % 8) of the tile's 4 x 32 grid positions (columns >= W are padding)
+            const int qrow = G.colblk ? I.qr0 + (lane >> 3) : I.qr0 + qi / G.W;
+            const int qcol = G.colblk ? ((warp & 3) << 3) + (lane & 7) : qi % G.W;
+            const bool valid = G.colblk ? (qrow <= I.qr1 && qcol < G.W) : (qi < I.nq);
             const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
             const int c_lo = qcol - G.radius;
             const int c_lo_cl = max(c_lo, 0), c_hi_cl = min(qcol + G.radius, G.W - 1);
+            // key columns any query of this warp can see: only these are read from TMEM.  Raster tiles: (nearly) the whole
+            // key row; column-blocked tiles: 8 + 2 * radius columns at most (20 of 28 at radius 6, 14 / 10 at the borders)
+            const int wc_lo = __reduce_min_sync(0xffffffffu, valid ? c_lo_cl : 0x7fffffff);
+            const int wc_hi = __reduce_max_sync(0xffffffffu, valid ? c_hi_cl : -1);
             float thr = (G.flags & 2) ? INFINITY : -INFINITY;      // debug flags (TIMET_TC_PFLAGS): 1 no scan, 2 scan without appends, 4 TMEM loads only
             int cnt = 0, lost = 0;
 
@@ -279,21 +297,21 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     // pick up the other groups' progress (one LDS per key row): the four groups of a query raise one threshold
                     if (!(G.flags & 64)) thr = fmaxf(thr, thr_dec(thr_cur[qi]));
                     const int code_row = (((G.flags & 8) ? ci : I.nctx - 1 - ci) << 10) | ((kr - r_lo) << 5);
-                    for (int cb = 0; cb < G.W; cb += 16) {
-                        int col0 = rr * G.W + cb;
-                        const int shift = max(0, col0 + 16 - G.buf_cols);
+                    // the warp's column range [wc_lo, wc_hi] in chunks of 16, 8 or 4 TMEM columns (13+ left: 16, 5+: 8, else 4)
+                    for (int c = wc_lo; c <= wc_hi;) {
+                        const int rem = wc_hi - c + 1;
+                        const int ne = rem >= 13 ? 16 : (rem >= 5 ? 8 : 4);
+                        int col0 = rr * G.W + c;
+                        const int shift = max(0, col0 + ne - G.buf_cols);     // keep the load inside the accumulator buffer
                         col0 -= shift;
-                        const int cb_eff = cb - shift;
-                        uint32_t r[16];
-                        ptx::tmem_ld_32x16(t_acc + (uint32_t)col0, r);
-                        const int lo = max(c_lo_cl - cb_eff, shift), hi = min(c_hi_cl - cb_eff, 15);
+                        const int cb_eff = c - shift;
+                        c += ne;
+                        const int lo = max(c_lo_cl - cb_eff, shift), hi = min(c_hi_cl - cb_eff, ne - 1);
                         uint32_t wmask = 0u;
                         if (row_ok && hi >= lo) wmask = (0xFFFFu >> (15 - hi)) & (0xFFFFu << lo) & 0xFFFFu;
                         const uint32_t code0 = (uint32_t)(code_row + (cb_eff - c_lo));
                         uint32_t slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
-                        ptx::tmem_ld_wait();
-                        if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[5]), "r"(r[10]), "r"(r[15])); continue; }
-                        // two runs of 8 offers, each followed by a capacity check: a list holds TC_CAP = 32 entries and at
+                        // runs of at most 8 offers, each followed by a capacity check: a list holds TC_CAP = 32 entries and at
                         // most 24 when a run starts (compaction leaves <= 16), so a run can never overflow it
 #define TC_CHECK()                                                                       \
     if (__any_sync(0xffffffffu, slot > slot_lim)) {                                      \
@@ -303,12 +321,33 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;                                    \
         if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));                         \
     }
-                        tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
-                        tc_offer4<4>(slot, r[4], r[5], r[6], r[7], thr, wmask, code0);
-                        TC_CHECK()
-                        tc_offer4<8>(slot, r[8], r[9], r[10], r[11], thr, wmask, code0);
-                        tc_offer4<12>(slot, r[12], r[13], r[14], r[15], thr, wmask, code0);
-                        TC_CHECK()
+                        if (ne == 16) {
+                            uint32_t r[16];
+                            ptx::tmem_ld_32x16(t_acc + (uint32_t)col0, r);
+                            ptx::tmem_ld_wait();
+                            if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[5]), "r"(r[10]), "r"(r[15])); continue; }
+                            tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
+                            tc_offer4<4>(slot, r[4], r[5], r[6], r[7], thr, wmask, code0);
+                            TC_CHECK()
+                            tc_offer4<8>(slot, r[8], r[9], r[10], r[11], thr, wmask, code0);
+                            tc_offer4<12>(slot, r[12], r[13], r[14], r[15], thr, wmask, code0);
+                            TC_CHECK()
+                        } else if (ne == 8) {
+                            uint32_t r[8];
+                            ptx::tmem_ld_32x8(t_acc + (uint32_t)col0, r);
+                            ptx::tmem_ld_wait();
+                            if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[3]), "r"(r[5]), "r"(r[7])); continue; }
+                            tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
+                            tc_offer4<4>(slot, r[4], r[5], r[6], r[7], thr, wmask, code0);
+                            TC_CHECK()
+                        } else {
+                            uint32_t r[4];
+                            ptx::tmem_ld_32x4(t_acc + (uint32_t)col0, r);
+                            ptx::tmem_ld_wait();
+                            if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])); continue; }
+                            tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
+                            TC_CHECK()
+                        }
 #undef TC_CHECK
                         cnt = (int)((slot - list) / TC_SLOT_STRIDE);
                     }
@@ -351,7 +390,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 cnt = min(tot, TC_CAP);
                 tc_compact(list0, cnt, thr, lost, G.topk, FF_CAND_STORE);
                 if (valid) {
-                    const int64_t q = ((int64_t)I.clip * G.nT + (I.t - G.t_begin)) * G.N + I.qr0 * G.W + qi;
+                    const int64_t q = ((int64_t)I.clip * G.nT + (I.t - G.t_begin)) * G.N + qrow * G.W + qcol;
                     uint32_t *dst = cand + q * FF_CAND_STORE;
 #pragma unroll
                     for (int s4 = 0; s4 < FF_CAND_STORE; s4 += 4) {
@@ -394,7 +433,14 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
     const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
     CUtensorMap map_a, map_b;
     int rc;
-    if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+    // column-blocked query tiles (see the kernel): grids 26..32 patches wide whose tiles are 4 grid rows, resident A.
+    // TIMET_TC_PFLAGS & 256 keeps the raster tile.
+    G.colblk = (G.a_resident && G.W >= 26 && G.W <= 32 && G.QR == 4 && !(G.flags & 256)) ? 1 : 0;
+    if (G.colblk) {
+        if ((rc = tc_make_map_colblk(&map_a, fn16, (int64_t)p.n_clips * p.n_frames * G.H, L.Dp, G.W)) != TIMET_OK) return rc;
+    } else {
+        if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+    }
     if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
     const size_t smem = persist_smem_bytes(G);
     auto kern = E.tc_dyn ? ff_tc_persist_kernel<true> : ff_tc_persist_kernel<false>;

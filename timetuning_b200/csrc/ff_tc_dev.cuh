@@ -27,6 +27,7 @@ struct TcGeom {
     int nbuf, buf_cols, nstages;   // TMEM accumulator buffers (4 x 128 or 2 x 256 columns), B ring depth
     int clip_group;           // clips whose tiles are launched together (L2 locality); env TIMET_TC_CLIP_GROUP
     int flags;                // debug (env TIMET_TC_FLAGS): 1 = epilogue releases tiles unscanned, 2 = scan but never append
+    int colblk;               // persistent kernel: query tile rows arranged as 4 column blocks of 4 x 8 queries (ff_tc3.cu)
     int64_t total_tiles;
 };
 
@@ -177,5 +178,6 @@ __device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, 
 bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G);
 size_t tc_smem_bytes(const TcGeom &G);
 int tc_make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int box_rows);
+int tc_make_map_colblk(CUtensorMap *m, const void *base, int64_t grid_rows, int Dp, int grid_w);
 
 }  // namespace timet

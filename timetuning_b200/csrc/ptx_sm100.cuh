@@ -81,6 +81,14 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// 3-D tiled load: coordinates (c0 = innermost element index, c1 = row, c2 = row group)
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05: TMEM allocation
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_result) {   // one full warp
@@ -150,6 +158,19 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
+}
+// 32 lanes x 8 / x 4 consecutive 32-bit columns (tails of a column range that is not a multiple of 16)
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
