@@ -25,7 +25,8 @@
 //
 // TIMET_TC_PFLAGS (attribution switches, profiles/tc_kernel_time.py): 1 release tiles unscanned, 2 scan without appends,
 // 4 TMEM loads only, 8 oldest-first context order, 32 nanosleep back-off while polling tmem_full, 64 shared threshold read
-// once per tile instead of once per key row, 128 each TMEM buffer scanned by its own two groups only.
+// once per tile instead of once per key row, 128 each TMEM buffer scanned by its own two groups only, 256 raster query tiles
+// (no column blocks), 512 epilogue waits for a key tile with a suspend-time hint.
 #include <stdlib.h>
 
 #include "ff_tc_dev.cuh"
@@ -266,15 +267,25 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
             const int c_lo = qcol - G.radius;
             const int c_lo_cl = max(c_lo, 0), c_hi_cl = min(qcol + G.radius, G.W - 1);
-            // key columns any query of this warp can see: only these are read from TMEM.  Raster tiles: (nearly) the whole
-            // key row; column-blocked tiles: 8 + 2 * radius columns at most (20 of 28 at radius 6, 14 / 10 at the borders)
+            // Key columns / key rows any query of this warp can see (warp-uniform): only these are read from TMEM.  Raster tiles:
+            // (nearly) the whole key row; column-blocked tiles: 8 + 2 * radius columns at most (20 of 28 at radius 6, 14 / 10
+            // at the borders).  The column range is walked in chunks of 16 / 8 / 4 TMEM columns; its width is rounded up to a
+            // multiple of 4 and, where that would run past the key row, moved left (the extra columns are outside every
+            // lane's window).  M = this lane's window as a bit mask over the key columns (W <= 64).
             const int wc_lo = __reduce_min_sync(0xffffffffu, valid ? c_lo_cl : 0x7fffffff);
             const int wc_hi = __reduce_max_sync(0xffffffffu, valid ? c_hi_cl : -1);
+            const int wr_lo = __reduce_min_sync(0xffffffffu, valid ? max(r_lo, I.kr_lo) : 0x7fffffff);
+            const int wr_hi = __reduce_max_sync(0xffffffffu, valid ? min(r_hi, I.kr_hi) : -1);
+            const int width = (wc_hi >= wc_lo) ? ((wc_hi - wc_lo + 4) & ~3) : 0;
+            const int cstart = max(0, min(wc_lo, G.W - width));
+            const unsigned long long M = valid ? (((2ull << c_hi_cl) - 1ull) & ~((1ull << c_lo_cl) - 1ull)) : 0ull;
             float thr = (G.flags & 2) ? INFINITY : -INFINITY;      // debug flags (TIMET_TC_PFLAGS): 1 no scan, 2 scan without appends, 4 TMEM loads only
             int cnt = 0, lost = 0;
+            uint32_t slot = list;                                  // next free slot of my list (cnt is derived from it when needed)
 
             // first tile of this item that lands in my buffer: (gtile + j) % nbuf == mybuf
-            int j = share_tiles ? 0 : (int)(((uint32_t)mybuf + (uint32_t)G.nbuf - (gtile % (uint32_t)G.nbuf)) % (uint32_t)G.nbuf);
+            const uint32_t nbuf_mask = (uint32_t)G.nbuf - 1u, nbuf_sh = (G.nbuf == 4) ? 2u : 1u;
+            int j = share_tiles ? 0 : (int)(((uint32_t)mybuf - gtile) & nbuf_mask);
             const int jstep = share_tiles ? 1 : G.nbuf;
             int ci = 0, ch = j;
             while (ch >= I.nchunks) { ch -= I.nchunks; ++ci; }
@@ -282,37 +293,36 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int kr_start = I.kr_lo + ch * G.RPC;
                 const int rc = min(G.RPC, I.kr_hi + 1 - kr_start);
                 const uint32_t tile_no = gtile + (uint32_t)j;                      // running tile count of this CTA
-                const int buf = share_tiles ? (int)(tile_no % (uint32_t)G.nbuf) : mybuf;
-                const uint32_t use = tile_no / (uint32_t)G.nbuf;
+                const int buf = (int)(tile_no & nbuf_mask);
+                const uint32_t use = tile_no >> nbuf_sh;
                 const uint32_t t_acc = tmem_base + (uint32_t)(buf * G.buf_cols) + lane_base;
-                if (lane == 0) { if (G.flags & 32) ptx::mbar_wait_sleep(&ctl->tmem_full[buf], use & 1u, 64); else ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u); }
+                if (lane == 0) {
+                    if (G.flags & 32) ptx::mbar_wait_sleep(&ctl->tmem_full[buf], use & 1u, 64);
+                    else if (G.flags & 512) ptx::mbar_wait_hint(&ctl->tmem_full[buf], use & 1u, 4000);
+                    else ptx::mbar_wait(&ctl->tmem_full[buf], use & 1u);
+                }
                 __syncwarp();
                 ptx::tc_fence_after();
                 thr = fmaxf(thr, thr_dec(thr_cur[qi]));
-                for (int rr = 0; rr < ((G.flags & 1) ? 0 : rc); ++rr) {
-                    if (share_tiles ? ((rr & 3) != g) : (row_par >= 0 && (rr & 1) != row_par)) continue;
+                // my key rows of this tile: rows [rlo_t, rhi_t] some lane can see, dealt round-robin to the four groups
+                // (or, with the buffer-owning mapping, to the two groups of the buffer)
+                // (a warp whose lanes are all padding has the empty range wr_lo > wr_hi: no rows)
+                const bool scan = wr_hi >= wr_lo && !(G.flags & 1);
+                const int rlo_t = scan ? max(0, wr_lo - kr_start) : 0, rhi_t = scan ? min(rc - 1, wr_hi - kr_start) : -1;
+                int rr, rstep;
+                if (share_tiles) { rstep = 4; rr = rlo_t + ((g - rlo_t) & 3); }
+                else if (row_par >= 0) { rstep = 2; rr = rlo_t + ((row_par - rlo_t) & 1); }
+                else { rstep = 1; rr = rlo_t; }
+                const int ctx_code = ((G.flags & 8) ? ci : I.nctx - 1 - ci) << 10;
+                for (; rr <= rhi_t; rr += rstep) {
                     const int kr = kr_start + rr;
-                    const bool row_ok = valid && kr >= r_lo && kr <= r_hi;
-                    if (!__any_sync(0xffffffffu, row_ok)) continue;
+                    const unsigned long long Mr = (kr >= r_lo && kr <= r_hi) ? M : 0ull;
                     // pick up the other groups' progress (one LDS per key row): the four groups of a query raise one threshold
                     if (!(G.flags & 64)) thr = fmaxf(thr, thr_dec(thr_cur[qi]));
-                    const int code_row = (((G.flags & 8) ? ci : I.nctx - 1 - ci) << 10) | ((kr - r_lo) << 5);
-                    // the warp's column range [wc_lo, wc_hi] in chunks of 16, 8 or 4 TMEM columns (13+ left: 16, 5+: 8, else 4)
-                    for (int c = wc_lo; c <= wc_hi;) {
-                        const int rem = wc_hi - c + 1;
-                        const int ne = rem >= 13 ? 16 : (rem >= 5 ? 8 : 4);
-                        int col0 = rr * G.W + c;
-                        const int shift = max(0, col0 + ne - G.buf_cols);     // keep the load inside the accumulator buffer
-                        col0 -= shift;
-                        const int cb_eff = c - shift;
-                        c += ne;
-                        const int lo = max(c_lo_cl - cb_eff, shift), hi = min(c_hi_cl - cb_eff, ne - 1);
-                        uint32_t wmask = 0u;
-                        if (row_ok && hi >= lo) wmask = (0xFFFFu >> (15 - hi)) & (0xFFFFu << lo) & 0xFFFFu;
-                        const uint32_t code0 = (uint32_t)(code_row + (cb_eff - c_lo));
-                        uint32_t slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;
-                        // runs of at most 8 offers, each followed by a capacity check: a list holds TC_CAP = 32 entries and at
-                        // most 24 when a run starts (compaction leaves <= 16), so a run can never overflow it
+                    const int code_row = ctx_code | ((kr - r_lo) << 5);
+                    const uint32_t t_row = t_acc + (uint32_t)(rr * G.W);
+                    // runs of at most 8 offers, each followed by a capacity check: a list holds TC_CAP = 32 entries and at
+                    // most 24 when a run starts (compaction leaves <= 16), so a run can never overflow it
 #define TC_CHECK()                                                                       \
     if (__any_sync(0xffffffffu, slot > slot_lim)) {                                      \
         const float before = thr;                                                        \
@@ -321,9 +331,14 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;                                    \
         if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));                         \
     }
-                        if (ne == 16) {
+                    for (int c = cstart, rem = width; rem > 0;) {
+                        const uint32_t wmask = (uint32_t)(Mr >> c);           // bit b: key column c + b is inside my window
+                        const uint32_t code0 = (uint32_t)(code_row + (c - c_lo));
+                        const uint32_t taddr = t_row + (uint32_t)c;
+                        if (rem >= 16) {
                             uint32_t r[16];
-                            ptx::tmem_ld_32x16(t_acc + (uint32_t)col0, r);
+                            ptx::tmem_ld_32x16(taddr, r);
+                            c += 16; rem -= 16;
                             ptx::tmem_ld_wait();
                             if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[5]), "r"(r[10]), "r"(r[15])); continue; }
                             tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
@@ -332,9 +347,10 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             tc_offer4<8>(slot, r[8], r[9], r[10], r[11], thr, wmask, code0);
                             tc_offer4<12>(slot, r[12], r[13], r[14], r[15], thr, wmask, code0);
                             TC_CHECK()
-                        } else if (ne == 8) {
+                        } else if (rem >= 8) {
                             uint32_t r[8];
-                            ptx::tmem_ld_32x8(t_acc + (uint32_t)col0, r);
+                            ptx::tmem_ld_32x8(taddr, r);
+                            c += 8; rem -= 8;
                             ptx::tmem_ld_wait();
                             if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[3]), "r"(r[5]), "r"(r[7])); continue; }
                             tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
@@ -342,15 +358,15 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                             TC_CHECK()
                         } else {
                             uint32_t r[4];
-                            ptx::tmem_ld_32x4(t_acc + (uint32_t)col0, r);
+                            ptx::tmem_ld_32x4(taddr, r);
+                            c += 4; rem -= 4;
                             ptx::tmem_ld_wait();
                             if (G.flags & 4) { asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])); continue; }
                             tc_offer4<0>(slot, r[0], r[1], r[2], r[3], thr, wmask, code0);
                             TC_CHECK()
                         }
-#undef TC_CHECK
-                        cnt = (int)((slot - list) / TC_SLOT_STRIDE);
                     }
+#undef TC_CHECK
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -358,6 +374,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 ch += jstep;
                 while (ch >= I.nchunks) { ch -= I.nchunks; ++ci; }
             }
+            cnt = (int)((slot - list) / TC_SLOT_STRIDE);
             gtile += (uint32_t)I.ntiles;
 
             // ---- final phase of the item (the MMA warp is already working on the next one)
@@ -424,6 +441,9 @@ static size_t persist_smem_bytes(const TcGeom &G) {
 int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
     TcGeom G;
     if (!tc_geometry(p, L, &G)) return TIMET_ERR_UNSUPPORTED;
+    // the epilogue keeps a lane's window as a 64-bit column mask and may read up to 3 TMEM columns past a key row whose
+    // width is not a multiple of 4: wider grids / exactly filled buffers go to the per-item kernel
+    if (G.W > 64 || ((G.W & 3) && G.NT + 3 > G.buf_cols)) return TIMET_ERR_UNSUPPORTED;
     G.nstages = TC_MAX_STAGES;
     const EnvCfg &E = env_cfg();
     G.flags = E.tc_pflags;

@@ -56,6 +56,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         }
     }
 }
+// try_wait with a suspend-time hint: the warp may stay suspended in hardware for up to `ns` before the instruction returns
+// false, so a long wait costs a handful of loop iterations instead of one every few dozen cycles
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, ns)) {
+        if (++spins > (1u << 24)) {
+            printf("timet: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+                   (void *)bar, parity);
+            __trap();
+        }
+    }
+}
 // Polite variant for many-waiter barriers: sleeps between polls so that the pollers leave the issue slots to the others
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
     uint32_t spins = 0;
