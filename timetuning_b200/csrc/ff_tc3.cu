@@ -26,7 +26,8 @@
 // TIMET_TC_PFLAGS (attribution switches, profiles/tc_kernel_time.py): 1 release tiles unscanned, 2 scan without appends,
 // 4 TMEM loads only, 8 oldest-first context order, 32 nanosleep back-off while polling tmem_full, 64 shared threshold read
 // once per tile instead of once per key row, 128 each TMEM buffer scanned by its own two groups only, 256 raster query tiles
-// (no column blocks), 512 epilogue waits for a key tile with a suspend-time hint.
+// (no column blocks), 512 epilogue waits for a key tile with a suspend-time hint, 1024 no final merge / publish, 2048 full lists are
+// emptied instead of compacted (1024 / 2048: timing attribution only, wrong results), 8192 no compaction while waiting for a key tile.
 #include <stdlib.h>
 
 #include "ff_tc_dev.cuh"
@@ -282,6 +283,8 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             float thr = (G.flags & 2) ? INFINITY : -INFINITY;      // debug flags (TIMET_TC_PFLAGS): 1 no scan, 2 scan without appends, 4 TMEM loads only
             int cnt = 0, lost = 0;
             uint32_t slot = list;                                  // next free slot of my list (cnt is derived from it when needed)
+            uint32_t slot_cmp = list;                              // ... right after the last compaction
+            constexpr uint32_t OPP_MIN = 6;
 
             // first tile of this item that lands in my buffer: (gtile + j) % nbuf == mybuf
             const uint32_t nbuf_mask = (uint32_t)G.nbuf - 1u, nbuf_sh = (G.nbuf == 4) ? 2u : 1u;
@@ -296,6 +299,19 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 const int buf = (int)(tile_no & nbuf_mask);
                 const uint32_t use = tile_no >> nbuf_sh;
                 const uint32_t t_acc = tmem_base + (uint32_t)(buf * G.buf_cols) + lane_base;
+                // The key tile is usually not there yet (the MMA side is the slower one): use the wait to compact the list
+                // and raise the threshold, so that the capacity check inside the scan -- which holds the TMEM buffer while it
+                // compacts -- rarely fires.  Only when some lane appended OPP_MIN entries since its last compaction.
+                if (!(G.flags & 8192)) {
+                    const bool there = __any_sync(0xffffffffu, lane == 0 && ptx::mbar_try_wait(&ctl->tmem_full[buf], use & 1u));
+                    if (!there && __any_sync(0xffffffffu, slot >= slot_cmp + OPP_MIN * TC_SLOT_STRIDE)) {
+                        const float before = thr;
+                        cnt = (int)((slot - list) / TC_SLOT_STRIDE);
+                        tc_compact(list, cnt, thr, lost, G.topk, half);
+                        slot = slot_cmp = list + (uint32_t)cnt * TC_SLOT_STRIDE;
+                        if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));
+                    }
+                }
                 if (lane == 0) {
                     if (G.flags & 32) ptx::mbar_wait_sleep(&ctl->tmem_full[buf], use & 1u, 64);
                     else if (G.flags & 512) ptx::mbar_wait_hint(&ctl->tmem_full[buf], use & 1u, 4000);
@@ -325,10 +341,11 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     // most 24 when a run starts (compaction leaves <= 16), so a run can never overflow it
 #define TC_CHECK()                                                                       \
     if (__any_sync(0xffffffffu, slot > slot_lim)) {                                      \
+        if (G.flags & 2048) { slot = list; continue; }                                   \
         const float before = thr;                                                        \
         cnt = (int)((slot - list) / TC_SLOT_STRIDE);                                     \
         tc_compact(list, cnt, thr, lost, G.topk, half);                                  \
-        slot = list + (uint32_t)cnt * TC_SLOT_STRIDE;                                    \
+        slot = slot_cmp = list + (uint32_t)cnt * TC_SLOT_STRIDE;                         \
         if (thr > before) atomicMax(&thr_cur[qi], thr_enc(thr));                         \
     }
                     for (int c = cstart, rem = width; rem > 0;) {
@@ -378,6 +395,11 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             gtile += (uint32_t)I.ntiles;
 
             // ---- final phase of the item (the MMA warp is already working on the next one)
+            if (G.flags & 1024) {                                      // attribution: no merge, nothing published
+                if (g == 1) ctl->thr_sh[(k + 1u) & 1u][qi] = thr_enc(-INFINITY);
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                continue;
+            }
             {
                 const float before = thr;
                 tc_compact(list, cnt, thr, lost, G.topk, half);
