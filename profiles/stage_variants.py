@@ -7,8 +7,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = [{}, {"TIMET_GATHER_BATCH": "5"}, {"TIMET_GATHER_BATCH": "7"}, {"TIMET_SK_DUAL": "0"}, {"TIMET_SC_STAGES": "4"},
-            {"TIMET_SK_STREAMING": "1"}]
-extra = sys.argv[1:]
+            {"TIMET_SK_STREAMING": "1"}, {"TIMET_GATHER_L1": "0"}, {"TIMET_TC_PFLAGS": "256"}, {"TIMET_TC_PFLAGS": "8192"}]
+extra = [a for a in sys.argv[1:] if not a.startswith("--only=")]
+only = [a[7:].split(",") for a in sys.argv[1:] if a.startswith("--only=")]
+if only:      # --only=TIMET_FIN_BLOCKED,... : the default plus the variants that set one of these switches
+    VARIANTS = [v for v in VARIANTS if not v or any(k in only[0] for k in v)]
 for env in VARIANTS:
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-e2e",
                           "--no-cpu-baseline", *extra], env=dict(os.environ, **env), capture_output=True, text=True)

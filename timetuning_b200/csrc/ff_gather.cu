@@ -44,7 +44,11 @@ __device__ __forceinline__ void ga_fma(float4 &a, float w, const float4 l) {
 
 // acc += sum_m w[m] * labels_row(k[m]) for the n_c (<= 32) entries held by the lanes of the warp (lane m: entry m).
 // GB gathered rows are in flight together (coherent L2 loads: earlier frames were written by other CTAs of this launch).
-template <typename V, int GB>
+// L1: gathered rows may be served from L1.  Safe when no 128-byte line holds data of two frames (see the launcher): a row is
+// written once, in the phase of its frame, and only read in later phases (after a cluster barrier / a kernel boundary), so
+// an SM never caches a line before its last write.  Neighbouring queries gather neighbouring rows: without L1 every one of
+// them goes to L2.
+template <typename V, int GB, bool L1>
 __device__ __forceinline__ void ga_rows(V &acc0, V &acc1, float w_c, int32_t k_c, int n_c, const float *clip_base, int C, int c,
                                         int c2, bool one, bool two) {
     for (int m0 = 0; m0 < n_c; m0 += GB) {
@@ -57,8 +61,8 @@ __device__ __forceinline__ void ga_rows(V &acc0, V &acc1, float w_c, int32_t k_c
             const int32_t km = __shfl_sync(0xffffffffu, k_c, m);
             const V *row = reinterpret_cast<const V *>(clip_base + (int64_t)km * C);
             const bool on = m0 + u < n_c;
-            l0[u] = (on && one) ? __ldcg(row + c) : ga_zero<V>();
-            l1[u] = (on && two) ? __ldcg(row + c2) : ga_zero<V>();
+            l0[u] = (on && one) ? (L1 ? __ldca(row + c) : __ldcg(row + c)) : ga_zero<V>();
+            l1[u] = (on && two) ? (L1 ? __ldca(row + c2) : __ldcg(row + c2)) : ga_zero<V>();
         }
 #pragma unroll
         for (int u = 0; u < GB; ++u) {
@@ -76,7 +80,7 @@ __device__ __noinline__ void ga_rows_wide(V &acc0, V &acc1, const float *__restr
         const bool in = base + lane < n_row;
         const float w_c = in ? __ldg(wide_w + wide_off + base + lane) : 0.f;
         const int32_t k_c = in ? __ldg(wide_k + wide_off + base + lane) : 0;
-        ga_rows<V, 2>(acc0, acc1, w_c, k_c, min(32, n_row - base), clip_base, C, c, c2, one, two);
+        ga_rows<V, 2, false>(acc0, acc1, w_c, k_c, min(32, n_row - base), clip_base, C, c, c2, one, two);
     }
 }
 
@@ -86,7 +90,7 @@ __device__ __noinline__ void ga_rows_wide(V &acc0, V &acc1, const float *__restr
 // launch).  The next query's sparse row is prefetched while the current one is gathered.
 // CLUSTER = false: the same body for ONE target frame per launch with `vcs` plain CTAs per clip (few clips: a
 // cluster of 8 CTAs per clip would leave most SMs idle; frames then cost one launch each).
-template <typename V, bool CLUSTER, int GB>
+template <typename V, bool CLUSTER, int GB, bool L1>
 __global__ void __launch_bounds__(GA_THREADS, 2)
 ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const float *__restrict__ sel_w,
                  const int32_t *__restrict__ sel_k, const int32_t *__restrict__ sel_cnt, const float *__restrict__ wide_w,
@@ -127,7 +131,7 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
                 // every lane holds the same cnt; taking it from a warp collective tells the compiler so (no per-shuffle
                 // reconvergence code around the loop below)
                 const int cnt_u = __reduce_max_sync(0xffffffffu, cnt);
-                ga_rows<V, GB>(acc0, acc1, w_l, k_l, cnt_u, clip_base, C, c, c2, one, two);
+                ga_rows<V, GB, L1>(acc0, acc1, w_l, k_l, cnt_u, clip_base, C, c, c2, one, two);
                 if (cnt_u < 0)   // wide row (more than kw survivors: exact tie sets): -cnt entries in the pool at offset sel_k[0]
                     ga_rows_wide<V>(acc0, acc1, wide_w, wide_k, __shfl_sync(0xffffffffu, k_l, 0), -cnt_u, clip_base, C, c, c2, one, two, lane);
                 if (one) dst[c] = acc0;
@@ -158,7 +162,7 @@ ff_gather_kernel(float *__restrict__ labels, int64_t *__restrict__ hard, const f
     }
 }
 
-template <int GBSEL>
+template <int GBSEL, bool L1>
 static int ff_gather_launch_gb(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
                                cudaStream_t st) {
     const float *sel_w = reinterpret_cast<const float *>(ws + L.off_sel_w);
@@ -185,10 +189,10 @@ static int ff_gather_launch_gb(const timet_ff_params &p, const FFLayout &L, floa
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         if (vec)
-            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4, true, GBSEL>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float4, true, GBSEL, L1>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                           L.nT, L.kw, tb, tb, nfr - 1, cs));
         else
-            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float, true, 4>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            TIMET_CUDA(cudaLaunchKernelEx(&cfg, ff_gather_kernel<float, true, 4, false>, labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                           L.nT, L.kw, tb, tb, nfr - 1, cs));
         TIMET_LAUNCHED();
         return TIMET_OK;
@@ -200,10 +204,10 @@ static int ff_gather_launch_gb(const timet_ff_params &p, const FFLayout &L, floa
     if (vcs < 1) vcs = 1;
     for (int t = tb; t < nfr; ++t) {
         if (vec)
-            ff_gather_kernel<float4, false, GBSEL><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            ff_gather_kernel<float4, false, GBSEL, L1><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                                                                   L.nT, L.kw, tb, t, t, vcs);
         else
-            ff_gather_kernel<float, false, 4><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
+            ff_gather_kernel<float, false, 4, false><<<p.n_clips * vcs, GA_THREADS, 0, st>>>(labels, hard, sel_w, sel_k, sel_cnt, wide_w, wide_k, nfr, L.N, nch,
                                                                                  L.nT, L.kw, tb, t, t, vcs);
         TIMET_LAUNCHED();
     }
@@ -216,9 +220,16 @@ static int ff_gather_launch_gb(const timet_ff_params &p, const FFLayout &L, floa
 int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels, int64_t *hard, const char *ws,
                      cudaStream_t st) {
     const int gb = env_cfg().gather_batch ? env_cfg().gather_batch : (p.topk == 5 ? 5 : 4);
-    if (gb == 5) return ff_gather_launch_gb<5>(p, L, labels, hard, ws, st);
-    if (gb >= 7) return ff_gather_launch_gb<7>(p, L, labels, hard, ws, st);
-    return ff_gather_launch_gb<4>(p, L, labels, hard, ws, st);
+    // L1-cached row loads only when a frame of labels is a whole number of 128-byte lines (no line shared by two frames)
+    const bool l1 = env_cfg().gather_l1 && ((int64_t)L.N * p.n_channels * 4) % 128 == 0 && (reinterpret_cast<uintptr_t>(labels) & 127) == 0;
+    if (l1) {
+        if (gb == 5) return ff_gather_launch_gb<5, true>(p, L, labels, hard, ws, st);
+        if (gb >= 7) return ff_gather_launch_gb<7, true>(p, L, labels, hard, ws, st);
+        return ff_gather_launch_gb<4, true>(p, L, labels, hard, ws, st);
+    }
+    if (gb == 5) return ff_gather_launch_gb<5, false>(p, L, labels, hard, ws, st);
+    if (gb >= 7) return ff_gather_launch_gb<7, false>(p, L, labels, hard, ws, st);
+    return ff_gather_launch_gb<4, false>(p, L, labels, hard, ws, st);
 }
 
 }  // namespace timet
