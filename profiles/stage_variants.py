@@ -7,7 +7,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VARIANTS = [{}, {"TIMET_GATHER_BATCH": "5"}, {"TIMET_GATHER_BATCH": "7"}, {"TIMET_SK_DUAL": "0"}, {"TIMET_SC_STAGES": "4"},
-            {"TIMET_SK_STREAMING": "1"}, {"TIMET_GATHER_L1": "0"}, {"TIMET_TC_PFLAGS": "256"}, {"TIMET_TC_PFLAGS": "8192"}]
+            {"TIMET_SK_STREAMING": "1"}, {"TIMET_GATHER_L1": "0"}, {"TIMET_FIN_STAGED": "0"}, {"TIMET_TC_PFLAGS": "256"}, {"TIMET_TC_PFLAGS": "8192"}]
 extra = [a for a in sys.argv[1:] if not a.startswith("--only=")]
 only = [a[7:].split(",") for a in sys.argv[1:] if a.startswith("--only=")]
 if only:      # --only=TIMET_FIN_BLOCKED,... : the default plus the variants that set one of these switches

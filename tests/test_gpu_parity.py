@@ -261,6 +261,21 @@ def test_full_batch_properties_config2():
         check_soft(got, ref, taint, what=f"cfg2 clip {b}")
 
 
+@pytest.mark.parametrize("env", [{"TIMET_GATHER_L1": "0"}, {"TIMET_FIN_STAGED": "0"}, {"TIMET_GATHER_L1": "0", "TIMET_FIN_STAGED": "0"}],
+                         ids=lambda e: "+".join(f"{k[6:]}={v}" for k, v in e.items()))
+def test_gather_and_finalize_variants_are_bit_identical(timet_env, env):
+    """The label rows gathered through L1 / with L2-only loads and the exact re-evaluation from shared-memory staged rows /
+    from registers give the same bits (same per-lane chains, same order of the weighted sums)."""
+    bs, fs, sr, D, K = 6, 8, 28, 384, 200
+    N = sr * sr
+    feats = cu(synth.clip_features(bs, fs, sr, D, seed=31))
+    first = cu(np.stack([synth.soft_labels(N, K, seed=300 + b) for b in range(bs)]))
+    labels, hard = tb.propagate_labels_batched(feats, first, 7, 6, 5)
+    timet_env(**env)
+    labels_v, hard_v = tb.propagate_labels_batched(feats, first, 7, 6, 5)
+    assert torch.equal(labels_v, labels) and torch.equal(hard_v, hard)
+
+
 def test_davis_style_eval_config4_slice():
     """BASELINE configs[3] shapes (480p ViT-S/8 -> 60x60 grid, radius 12, top-k 7, n_last 7, C=11),
     first 10 frames of a synthetic video."""

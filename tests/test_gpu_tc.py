@@ -137,7 +137,10 @@ def test_tc_random_features_worst_case():
     {"TIMET_TC_PFLAGS": "128"},                 # every TMEM buffer scanned by its own two groups
     {"TIMET_TC_PFLAGS": "72"},                  # oldest-first contexts, threshold picked up per tile
     {"TIMET_TC_PFLAGS": "256"},                 # raster query tiles instead of column-blocked ones
-], ids=lambda e: "+".join(f"{k[9:]}={v}" for k, v in e.items()))
+    {"TIMET_TC_PFLAGS": "8192"},                # no compaction while waiting for a key tile
+    {"TIMET_TC_PFLAGS": "8576"},                # ... with raster tiles and buffer-owning groups
+    {"TIMET_FIN_STAGED": "0"},                  # exact re-evaluation from registers instead of cp.async-staged rows
+], ids=lambda e: "+".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_tc_kernel_variants_are_bit_identical(timet_env, env):
     """Every kernel variant / schedule behind the experiment switches nominates a superset of the exact
     top-k, so after the fp32 re-evaluation all of them reproduce the exact engine bit for bit."""

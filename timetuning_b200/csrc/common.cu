@@ -52,6 +52,7 @@ void env_reload() {
     e.sk_ustride = env_int("TIMET_SK_USTRIDE", 0);
     e.gather_batch = env_int("TIMET_GATHER_BATCH", 0);
     e.gather_l1 = env_int("TIMET_GATHER_L1", 1) != 0;
+    e.fin_staged = env_int("TIMET_FIN_STAGED", 1) != 0;
     e.sc_stages = env_int("TIMET_SC_STAGES", 0);
     const char *to = getenv("TIMET_P2P_TIMEOUT_S");
     e.p2p_timeout_s = (to && atof(to) > 0.0) ? atof(to) : 600.0;    // NCCL-like patience: rank skew of minutes is legal

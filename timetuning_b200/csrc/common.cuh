@@ -54,6 +54,7 @@ struct EnvCfg {
     int sk_ustride;                                                // 0 = default
     int sc_stages;                                                 // cosine-scores GEMM ring depth (2 = two CTAs per SM, default; 4)
     int gather_batch;                                              // gather: label rows in flight per batch (0 = by topk)
+    bool fin_staged;                                               // finalize: rows staged in shared memory with cp.async (default, dim <= 384)
     bool gather_l1;                                                // gather: label rows through L1 where that is safe (default)
     double p2p_timeout_s;                                          // peer-exchange / marginal wait time-out (seconds)
 };

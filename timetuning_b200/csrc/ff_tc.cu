@@ -341,13 +341,28 @@ __device__ __forceinline__ float fin_reduce4(const float (&acc)[4], int lane) {
     return v;
 }
 
-__global__ void __launch_bounds__(FIN_WARPS * 32, 4)
+// STAGED (rows of at most FIN_STAGE_N4 float4, i.e. dim <= 384): the query row and up to FIN_SB key rows of a query are
+// copied to the warp's slice of shared memory with cp.async -- every 16-byte piece of all six rows is in flight at once and
+// costs no register -- and the dot products then read shared memory.  The register form below can keep only part of a batch
+// in flight inside the 64 registers that four CTAs per SM allow (ptxas interleaves loads and fma chains: several dependent
+// L2 round trips per query); staged, a query with k = 5 candidates costs ONE round trip, at three CTAs per SM.  Same
+// per-lane fma chains, same butterfly: identical bits.
+constexpr int FIN_SB = 5;                      // key rows staged together
+constexpr int FIN_STAGE_N4 = 96;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+template <bool STAGED>
+__global__ void __launch_bounds__(FIN_WARPS * 32, STAGED ? 3 : 4)
 ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw, uint32_t w_magic,
                    const uint32_t *__restrict__ cand, const uint32_t *__restrict__ cand_meta,
                    float *__restrict__ sel_w, int32_t *__restrict__ sel_k, int32_t *__restrict__ sel_cnt,
                    unsigned long long *__restrict__ stats, int32_t *__restrict__ redo_list,
                    unsigned int *__restrict__ redo_count, uint32_t n_queries) {
     __shared__ unsigned long long s_stat[4];
+    extern __shared__ float4 fin_stage[];          // STAGED: [warp][1 + FIN_SB][n4]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
     __syncthreads();
@@ -402,7 +417,41 @@ ff_finalize_kernel(timet_ff_params p, int N, FFSrc S, int nT, int kw, uint32_t w
         // warp-cooperative canonical dot, four candidates at a time: the query row and the key rows of a batch are in
         // flight together
         float my_dot = 0.f;
-        for (int c0 = 0; c0 < nc; c0 += FIN_BATCH) {
+        if (STAGED) {
+            float4 *wq = fin_stage + (size_t)warp * (1 + FIN_SB) * n4;      // row 0: query, rows 1..FIN_SB: keys
+            __syncwarp();                                                  // the previous query's reads are done
+            for (int e = lane; e < n4; e += 32) cp_async16(wq + e, qrow + e);
+            for (int c0 = 0; c0 < nc; c0 += FIN_SB) {
+                const int nb = min(FIN_SB, nc - c0);
+                for (int u = 0; u < nb; ++u) {
+                    const int32_t row = __shfl_sync(0xffffffffu, krow, c0 + u);
+                    const float4 *kp = reinterpret_cast<const float4 *>(S.x + (int64_t)row * S.ld);
+                    float4 *dst = wq + (size_t)(1 + u) * n4;
+                    for (int e = lane; e < n4; e += 32) cp_async16(dst + e, kp + e);
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                for (int u0 = 0; u0 < nb; u0 += 4) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float4 *k0 = wq + (size_t)(1 + u0) * n4;
+                    const int nu = min(4, nb - u0);                       // warp-uniform
+#pragma unroll 3
+                    for (int e = lane; e < n4; e += 32) {
+                        const float4 x = wq[e];
+                        acc[0] = fma4_chain(acc[0], x, k0[e]);
+                        if (nu > 1) acc[1] = fma4_chain(acc[1], x, k0[n4 + e]);
+                        if (nu > 2) acc[2] = fma4_chain(acc[2], x, k0[2 * n4 + e]);
+                        if (nu > 3) acc[3] = fma4_chain(acc[3], x, k0[3 * n4 + e]);
+                    }
+                    const float red = fin_reduce4(acc, lane);
+                    const int u_me = lane - (c0 + u0);                    // candidate `lane` is accumulator u_me of this sub-batch
+                    const float mine = __shfl_sync(0xffffffffu, red, ((u_me & 2) << 3) | ((u_me & 1) << 3));
+                    if (u_me >= 0 && u_me < nu) my_dot = mine;
+                }
+                __syncwarp();                                              // before the next batch overwrites the key rows
+            }
+        }
+        for (int c0 = 0; !STAGED && c0 < nc; c0 += FIN_BATCH) {
             const float4 *kp[FIN_BATCH];
 #pragma unroll
             for (int u = 0; u < FIN_BATCH; ++u) {
@@ -650,7 +699,11 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float
     const int64_t blocks = (L.queries + FIN_QPB - 1) / FIN_QPB;
     TIMET_CHECK_ARG(L.queries < (1ll << 31), "ff_select: %lld queries exceed the 32-bit query index of the tensor-core engine", (long long)L.queries);
     const uint32_t w_magic = (uint32_t)((0x100000000ull + (uint64_t)p.grid_w - 1) / (uint64_t)p.grid_w);   // ceil(2^32 / W)
-    ff_finalize_kernel<<<(unsigned)blocks, FIN_WARPS * 32, 0, st>>>(
+    const bool staged = E.fin_staged && S.n4 <= FIN_STAGE_N4;
+    const size_t fin_smem = staged ? (size_t)FIN_WARPS * (1 + FIN_SB) * S.n4 * sizeof(float4) : 0;
+    auto fin = staged ? ff_finalize_kernel<true> : ff_finalize_kernel<false>;
+    if (fin_smem > 48 * 1024) TIMET_CUDA(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    fin<<<(unsigned)blocks, FIN_WARPS * 32, fin_smem, st>>>(
         p, L.N, S, L.nT, L.kw, w_magic, cand, meta, reinterpret_cast<float *>(ws + L.off_sel_w),
         reinterpret_cast<int32_t *>(ws + L.off_sel_k), reinterpret_cast<int32_t *>(ws + L.off_sel_cnt),
         reinterpret_cast<unsigned long long *>(ws + L.off_stats), redo_list, redo_count, (uint32_t)L.queries);
