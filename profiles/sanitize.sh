@@ -3,7 +3,7 @@
 #   bash profiles/sanitize.sh   ->  gpurun_out/r2_sanitizer_{memcheck,racecheck,synccheck}.log
 set -u
 CS=/usr/local/cuda/bin/compute-sanitizer
-TESTS="tests/test_gpu_ties.py tests/test_gpu_tc.py::test_tc_engine_is_bit_identical_to_exact tests/test_gpu_parity.py::test_timet_step_cfg1_golden tests/test_gpu_parity.py::test_sinkhorn_golden tests/test_gpu_parity.py::test_sinkhorn_strided_output_into_label_frames tests/test_gpu_parity.py::test_cosine_scores_multi_and_autograd tests/test_gpu_parity.py::test_non_square_grid_drop_ins tests/test_gpu_parity.py::test_eval_tail_upsample_argmax"
+TESTS="tests/test_gpu_ties.py tests/test_gpu_tc.py::test_tc_engine_is_bit_identical_to_exact tests/test_gpu_tc.py::test_tc_column_blocked_query_tiles tests/test_gpu_parity.py::test_timet_step_cfg1_golden tests/test_gpu_parity.py::test_sinkhorn_golden tests/test_gpu_parity.py::test_sinkhorn_strided_output_into_label_frames tests/test_gpu_parity.py::test_cosine_scores_multi_and_autograd tests/test_gpu_parity.py::test_non_square_grid_drop_ins tests/test_gpu_parity.py::test_eval_tail_upsample_argmax"
 for tool in memcheck racecheck synccheck; do
   $CS --tool $tool --error-exitcode 86 --print-limit 20 python -m pytest $TESTS -m gpu -q -x -p no:cacheprovider > gpurun_out/r2_sanitizer_$tool.log 2>&1
   echo "$tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/r2_sanitizer_$tool.log | tr '\n' ' ')"

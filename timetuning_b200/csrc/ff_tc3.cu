@@ -284,7 +284,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int cnt = 0, lost = 0;
             uint32_t slot = list;                                  // next free slot of my list (cnt is derived from it when needed)
             uint32_t slot_cmp = list;                              // ... right after the last compaction
-            constexpr uint32_t OPP_MIN = 6;
+            const uint32_t OPP_MIN = ((uint32_t)G.flags >> 16) ? ((uint32_t)G.flags >> 16) : 6u;   // experiments: TIMET_TC_PFLAGS bits 16+
 
             // first tile of this item that lands in my buffer: (gtile + j) % nbuf == mybuf
             const uint32_t nbuf_mask = (uint32_t)G.nbuf - 1u, nbuf_sh = (G.nbuf == 4) ? 2u : 1u;
