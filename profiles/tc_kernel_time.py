@@ -33,7 +33,7 @@ sel_ex = [plan.selection(c, t) for c in (0, 31) for t in (1, 7)]
 same = all(all(torch.equal(x, y) for x, y in zip(p, q)) for p, q in zip(sel_tc, sel_ex))
 print("kernel ms %%.4f  select ms %%.4f  identical=%%s  %%s" %% (sum(ks) / len(ks), sum(ss) / len(ss), same, st))
 ''' % ROOT
-VARIANTS = (("persistent", {}), ("raster-tiles", {"TIMET_TC_PFLAGS": "256"}), ("raster-noappend", {"TIMET_TC_PFLAGS": "258"}), ("wait-hint", {"TIMET_TC_PFLAGS": "512"}), ("no-wait-compaction", {"TIMET_TC_PFLAGS": "8192"}), ("opp-min-2", {"TIMET_TC_PFLAGS": str(2 << 16)}), ("opp-min-4", {"TIMET_TC_PFLAGS": str(4 << 16)}), ("opp-min-10", {"TIMET_TC_PFLAGS": str(10 << 16)}), ("opp-min-16", {"TIMET_TC_PFLAGS": str(16 << 16)}), ("no-final-merge", {"TIMET_TC_PFLAGS": "1024"}), ("no-inloop-compaction", {"TIMET_TC_PFLAGS": "2048"}), ("no-merge-no-compaction", {"TIMET_TC_PFLAGS": "3072"}), ("wait-sleep", {"TIMET_TC_PFLAGS": "32"}), ("thr-per-tile", {"TIMET_TC_PFLAGS": "64"}), ("static-schedule", {"TIMET_TC_DYN": "0"}), ("oldest-first", {"TIMET_TC_PFLAGS": "8"}),
+VARIANTS = (("persistent", {}), ("raster-tiles", {"TIMET_TC_PFLAGS": "256"}), ("raster-noappend", {"TIMET_TC_PFLAGS": "258"}), ("wait-hint", {"TIMET_TC_PFLAGS": "512"}), ("no-wait-compaction", {"TIMET_TC_PFLAGS": "8192"}), ("two-stage-ring", {"TIMET_TC_PFLAGS": "16384"}), ("two-stage-ring-mma-only", {"TIMET_TC_PFLAGS": "16385"}), ("two-stage-ring-noappend", {"TIMET_TC_PFLAGS": "16386"}), ("opp-min-2", {"TIMET_TC_PFLAGS": str(2 << 20)}), ("opp-min-4", {"TIMET_TC_PFLAGS": str(4 << 20)}), ("opp-min-10", {"TIMET_TC_PFLAGS": str(10 << 20)}), ("opp-min-16", {"TIMET_TC_PFLAGS": str(16 << 20)}), ("top-down-rows", {"TIMET_TC_PFLAGS": "32768"}), ("two-stage-top-down", {"TIMET_TC_PFLAGS": str(16384 + 32768)}), ("no-final-merge", {"TIMET_TC_PFLAGS": "1024"}), ("no-inloop-compaction", {"TIMET_TC_PFLAGS": "2048"}), ("no-merge-no-compaction", {"TIMET_TC_PFLAGS": "3072"}), ("wait-sleep", {"TIMET_TC_PFLAGS": "32"}), ("thr-per-tile", {"TIMET_TC_PFLAGS": "64"}), ("static-schedule", {"TIMET_TC_DYN": "0"}), ("oldest-first", {"TIMET_TC_PFLAGS": "8"}),
             ("thr-per-tile", {"TIMET_TC_PFLAGS": "64"}), ("groups-own-buffers", {"TIMET_TC_PFLAGS": "128"}), ("four-tmem-buffers", {"TIMET_TC_NBUF": "4"}), ("mma-only", {"TIMET_TC_PFLAGS": "1"}),
             ("scan-noappend", {"TIMET_TC_PFLAGS": "2"}), ("tmem-loads-only", {"TIMET_TC_PFLAGS": "4"}),
             ("per-tile", {"TIMET_TC_PERSIST": "0"}), ("per-tile-mma-only", {"TIMET_TC_PERSIST": "0", "TIMET_TC_FLAGS": "1"}),

@@ -140,6 +140,7 @@ def test_tc_random_features_worst_case():
     {"TIMET_TC_PFLAGS": "8192"},                # no compaction while waiting for a key tile
     {"TIMET_TC_PFLAGS": "8576"},                # ... with raster tiles and buffer-owning groups
     {"TIMET_FIN_STAGED": "0"},                  # exact re-evaluation from registers instead of cp.async-staged rows
+    {"TIMET_TC_PFLAGS": "16384"},               # query tile with its padding rows inside every K chunk, 32-slot lists, 2-stage key ring
 ], ids=lambda e: "+".join(f"{k[6:]}={v}" for k, v in e.items()))
 def test_tc_kernel_variants_are_bit_identical(timet_env, env):
     """Every kernel variant / schedule behind the experiment switches nominates a superset of the exact

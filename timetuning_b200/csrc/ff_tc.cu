@@ -555,9 +555,9 @@ int tc_make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int box_
 
 // Query-tile map of the column-blocked persistent kernel (ff_tc3.cu): the same fp16 rows viewed as
 // {Dp, grid_w patch columns, grid_rows = clips x frames x grid_h}; one box {64, 8, 4} fetches a 4 x 8 block of the patch
-// grid (8 consecutive columns of 4 consecutive grid rows) as 32 consecutive tile rows.  Columns >= grid_w and grid rows
-// past the end are out of bounds and arrive as zeros.
-int tc_make_map_colblk(CUtensorMap *m, const void *base, int64_t grid_rows, int Dp, int grid_w) {
+// grid (8 consecutive columns of 4 consecutive grid rows) as 32 consecutive tile rows; box_cols < 8 for the last, narrower
+// column block.  Columns >= grid_w and grid rows past the end are out of bounds and arrive as zeros.
+int tc_make_map_colblk(CUtensorMap *m, const void *base, int64_t grid_rows, int Dp, int grid_w, int box_cols) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -565,7 +565,7 @@ int tc_make_map_colblk(CUtensorMap *m, const void *base, int64_t grid_rows, int 
     }
     const cuuint64_t dims[3] = {(cuuint64_t)Dp, (cuuint64_t)grid_w, (cuuint64_t)grid_rows};
     const cuuint64_t strides[2] = {(cuuint64_t)Dp * sizeof(__half), (cuuint64_t)grid_w * Dp * sizeof(__half)};
-    const cuuint32_t box[3] = {64u, 8u, 4u};
+    const cuuint32_t box[3] = {64u, (cuuint32_t)box_cols, 4u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -609,7 +609,7 @@ bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G) {
     G->n_clips = p.n_clips; G->n_frames = p.n_frames; G->nT = L.nT; G->t_begin = p.t_begin;
     G->n_last = p.n_last_frames; G->radius = p.radius; G->topk = p.topk;
     G->flags = E.tc_flags;
-    G->colblk = 0;
+    G->colblk = 0; G->ncl = 8; G->a_chunk_bytes = 16384;
     G->clip_group = E.tc_clip_group >= 1 ? E.tc_clip_group : TC_CLIP_GROUP;
     G->total_tiles = (int64_t)p.n_clips * L.nT * G->tiles_per_frame;
     G->nstages = TC_MAX_STAGES;                                  // as deep a B ring as shared memory allows

@@ -84,9 +84,14 @@ __device__ __forceinline__ int64_t item_at(uint32_t k, int64_t total) {
     return (row0 < total && id < total) ? id : -1;
 }
 
-template <bool DYN>
+// CAP = slots per (query, group) candidate list (32, or 24 where the 16 KB that saves buy another stage of the key ring).
+// Column-blocked tiles store the last, narrower column block as 4 x ncl queries (map_a3: box {64, ncl, 4}) so that the
+// padding rows of the 128-row tile come last; the 64-wide K chunks of A then lie (96 + 4 ncl) * 128 bytes apart instead of
+// 16 KB, and the MMA's rows past that (the next chunk's first rows) only feed TMEM lanes nobody reads.
+template <bool DYN, int CAP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom G,
+ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a3,
+                     const __grid_constant__ CUtensorMap map_b, TcGeom G,
                      uint32_t *__restrict__ cand, uint32_t *__restrict__ cand_meta, unsigned int *__restrict__ next_item) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -94,9 +99,10 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const uint32_t b_stage_bytes = (uint32_t)G.NT * 128u;
     const uint32_t a_in_stage = G.a_resident ? 0u : 16384u;       // D > 384: the A chunk rides in front of every B chunk
     const uint32_t stage_bytes = b_stage_bytes + a_in_stage;
-    uint8_t *sB = sA + (G.a_resident ? (size_t)G.NKC * 16384 : 0);
+    const uint32_t a_chunk = (uint32_t)G.a_chunk_bytes;
+    uint8_t *sB = sA + (G.a_resident ? (size_t)G.NKC * a_chunk : 0);
     uint32_t *sList = reinterpret_cast<uint32_t *>(sB + (size_t)G.nstages * stage_bytes);
-    PsCtl *ctl = reinterpret_cast<PsCtl *>(sList + TC_GROUPS * TC_CAP * 128);
+    PsCtl *ctl = reinterpret_cast<PsCtl *>(sList + TC_GROUPS * CAP * 128);
     // roles: warps 0-15 = epilogue groups (TMEM lane quadrant = warp & 3), 16 = TMA producer, 17 = MMA issuer,
     // 18 = TMEM allocator, 19 = threshold init
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,6 +115,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 
     if (warp == W_PROD && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_a3);
         ptx::prefetch_tensormap(&map_b);
     }
     if (warp == W_MMA && lane == 0) {
@@ -153,15 +160,17 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             if (G.a_resident) {
                 ptx::mbar_wait(&ctl->a_free, (k & 1u) ^ 1u);          // every MMA of the previous item has read A
                 if (ptx::elect_one()) {
-                    ptx::mbar_expect_tx(&ctl->a_full, (uint32_t)G.NKC * 16384u);
+                    ptx::mbar_expect_tx(&ctl->a_full, G.colblk ? (uint32_t)G.NKC * (3u * 4096u + (uint32_t)G.ncl * 512u) : (uint32_t)G.NKC * 16384u);
                     if (G.colblk) {
                         // column-blocked query tile: quadrant w (tile rows 32w .. 32w+31 = the TMEM lanes of epilogue warps
                         // 4g+w) holds the 4 x 8 block of queries (grid rows qr0 .. qr0+3, columns 8w .. 8w+7); one 3-D box
                         // {64 elements, 8 patch columns, 4 grid rows} = 4 KB per quadrant and 64-wide K chunk
                         const int grow0 = (I.clip * G.n_frames + I.t) * G.H + I.qr0;
-                        for (int kc = 0; kc < G.NKC; ++kc)
-                            for (int w = 0; w < 4; ++w)
-                                ptx::tma_load_3d(sA + kc * 16384 + w * 4096, &map_a, kc * 64, 8 * w, grow0, &ctl->a_full);
+                        for (int kc = 0; kc < G.NKC; ++kc) {
+                            for (int w = 0; w < 3; ++w)
+                                ptx::tma_load_3d(sA + kc * a_chunk + w * 4096, &map_a, kc * 64, 8 * w, grow0, &ctl->a_full);
+                            ptx::tma_load_3d(sA + kc * a_chunk + 3 * 4096, &map_a3, kc * 64, 24, grow0, &ctl->a_full);   // 4 x ncl queries
+                        }
                     } else {
                         for (int kc = 0; kc < G.NKC; ++kc) ptx::tma_load_2d(sA + kc * 16384, &map_a, kc * 64, I.q_row0, &ctl->a_full);
                     }
@@ -213,7 +222,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * (uint32_t)G.buf_cols;
                 uint64_t da = da0;
-                for (int kc = 0; kc < G.NKC; ++kc, da += 16384 >> 4) {
+                for (int kc = 0; kc < G.NKC; ++kc, da += a_chunk >> 4) {
                     ptx::mbar_wait(&ctl->full[stage], phase);
                     ptx::tc_fence_after();
                     const uint64_t ds = db0 + (uint64_t)(stage * stage_step);
@@ -242,9 +251,14 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int qi = ((warp & 3) << 5) + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) << 5) << 16;
         const uint32_t list0 = ptx::smem_u32(sList + qi);
-        const uint32_t list = list0 + (uint32_t)g * TC_CAP * 128u * 4u;
-        constexpr int half = TC_CAP / 2;
-        const uint32_t slot_lim = list + (uint32_t)(TC_CAP - 8) * TC_SLOT_STRIDE;   // compaction trigger: more than 24 entries
+        const uint32_t list = list0 + (uint32_t)g * CAP * 128u * 4u;
+        constexpr int half = 16;                                       // entries a compaction may leave
+        const uint32_t slot_lim = list + (uint32_t)(CAP - 8) * TC_SLOT_STRIDE;      // compaction trigger: more than CAP - 8 entries
+        // column-blocked tiles: my position inside the tile's 4 x 32 grid positions (the last column block holds 4 x ncl queries)
+        const int cb_w = warp & 3;
+        const int cb_n = (cb_w == 3) ? G.ncl : 8;
+        const int cb_lr = lane / cb_n, cb_lc = cb_w * 8 + lane % cb_n;
+        const bool cb_ok = lane < 4 * cb_n;
         uint32_t gtile = 0;                                            // tiles issued before this item (all roles agree)
         for (uint32_t k = 0;; ++k) {
             int64_t id;
@@ -261,10 +275,10 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             const Item I = item_geom(G, id);
             uint32_t *thr_cur = ctl->thr_sh[k & 1u];
             // query of this thread (= TMEM lane qi): raster order inside the tile, or -- column-blocked tile -- position
-            // (lane / 8, 8 * quadrant + lane % 8) of the tile's 4 x 32 grid positions (columns >= W are padding)
-            const int qrow = G.colblk ? I.qr0 + (lane >> 3) : I.qr0 + qi / G.W;
-            const int qcol = G.colblk ? ((warp & 3) << 3) + (lane & 7) : qi % G.W;
-            const bool valid = G.colblk ? (qrow <= I.qr1 && qcol < G.W) : (qi < I.nq);
+            // (lane / 8, 8 * quadrant + lane % 8) of the tile's 4 x 32 grid positions; the last quadrant: (lane / ncl, 24 + lane % ncl)
+            const int qrow = G.colblk ? I.qr0 + cb_lr : I.qr0 + qi / G.W;
+            const int qcol = G.colblk ? cb_lc : qi % G.W;
+            const bool valid = G.colblk ? (cb_ok && qrow <= I.qr1 && qcol < G.W) : (qi < I.nq);
             const int r_lo = qrow - G.radius, r_hi = qrow + G.radius;
             const int c_lo = qcol - G.radius;
             const int c_lo_cl = max(c_lo, 0), c_hi_cl = min(qcol + G.radius, G.W - 1);
@@ -284,7 +298,7 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             int cnt = 0, lost = 0;
             uint32_t slot = list;                                  // next free slot of my list (cnt is derived from it when needed)
             uint32_t slot_cmp = list;                              // ... right after the last compaction
-            const uint32_t OPP_MIN = ((uint32_t)G.flags >> 16) ? ((uint32_t)G.flags >> 16) : 6u;   // experiments: TIMET_TC_PFLAGS bits 16+
+            const uint32_t OPP_MIN = ((uint32_t)G.flags >> 20) ? ((uint32_t)G.flags >> 20) : 6u;   // experiments: TIMET_TC_PFLAGS bits 20+
 
             // first tile of this item that lands in my buffer: (gtile + j) % nbuf == mybuf
             const uint32_t nbuf_mask = (uint32_t)G.nbuf - 1u, nbuf_sh = (G.nbuf == 4) ? 2u : 1u;
@@ -325,20 +339,25 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 // (a warp whose lanes are all padding has the empty range wr_lo > wr_hi: no rows)
                 const bool scan = wr_hi >= wr_lo && !(G.flags & 1);
                 const int rlo_t = scan ? max(0, wr_lo - kr_start) : 0, rhi_t = scan ? min(rc - 1, wr_hi - kr_start) : -1;
-                int rr, rstep;
-                if (share_tiles) { rstep = 4; rr = rlo_t + ((g - rlo_t) & 3); }
-                else if (row_par >= 0) { rstep = 2; rr = rlo_t + ((row_par - rlo_t) & 1); }
-                else { rstep = 1; rr = rlo_t; }
+                int rr, rstep, rsh;
+                if (share_tiles) { rstep = 4; rsh = 2; rr = rlo_t + ((g - rlo_t) & 3); }
+                else if (row_par >= 0) { rstep = 2; rsh = 1; rr = rlo_t + ((row_par - rlo_t) & 1); }
+                else { rstep = 1; rsh = 0; rr = rlo_t; }
+                // Rows nearest to the query tile first: the best matches sit there, so the threshold is close to final after
+                // the first row and the remaining rows of the tile append little.  A key chunk above the tile's centre is
+                // walked from its last row upwards.  (flags & 32768: always top-down.)
+                int n_rows = (rr <= rhi_t) ? ((rhi_t - rr) >> rsh) + 1 : 0;
+                if (2 * kr_start + rc <= 2 * I.qr0 + (I.qr1 - I.qr0 + 1) && !(G.flags & 32768)) { rr += (n_rows - 1) * rstep; rstep = -rstep; }
                 const int ctx_code = ((G.flags & 8) ? ci : I.nctx - 1 - ci) << 10;
-                for (; rr <= rhi_t; rr += rstep) {
+                for (; n_rows > 0; --n_rows, rr += rstep) {
                     const int kr = kr_start + rr;
                     const unsigned long long Mr = (kr >= r_lo && kr <= r_hi) ? M : 0ull;
                     // pick up the other groups' progress (one LDS per key row): the four groups of a query raise one threshold
                     if (!(G.flags & 64)) thr = fmaxf(thr, thr_dec(thr_cur[qi]));
                     const int code_row = ctx_code | ((kr - r_lo) << 5);
                     const uint32_t t_row = t_acc + (uint32_t)(rr * G.W);
-                    // runs of at most 8 offers, each followed by a capacity check: a list holds TC_CAP = 32 entries and at
-                    // most 24 when a run starts (compaction leaves <= 16), so a run can never overflow it
+                    // runs of at most 8 offers, each followed by a capacity check: a list holds CAP entries and at most
+                    // CAP - 8 when a run starts (a compaction leaves <= 16 <= CAP - 8), so a run can never overflow it
 #define TC_CHECK()                                                                       \
     if (__any_sync(0xffffffffu, slot > slot_lim)) {                                      \
         if (G.flags & 2048) { slot = list; continue; }                                   \
@@ -421,12 +440,12 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
             if (g > 0) {
                 for (int s = 0; s < cnt; ++s)
-                    if (off + s < TC_CAP) sts_u32(list0 + (uint32_t)(off + s) * TC_SLOT_STRIDE, lds_u32(list + s * TC_SLOT_STRIDE));
+                    if (off + s < CAP) sts_u32(list0 + (uint32_t)(off + s) * TC_SLOT_STRIDE, lds_u32(list + s * TC_SLOT_STRIDE));
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");            // (C) list 0 holds the merged candidates
             if (g == 0) {
-                lost = any_lost | (tot > TC_CAP ? 1 : 0);
-                cnt = min(tot, TC_CAP);
+                lost = any_lost | (tot > CAP ? 1 : 0);
+                cnt = min(tot, CAP);
                 tc_compact(list0, cnt, thr, lost, G.topk, FF_CAND_STORE);
                 if (valid) {
                     const int64_t q = ((int64_t)I.clip * G.nT + (I.t - G.t_begin)) * G.N + qrow * G.W + qcol;
@@ -454,9 +473,14 @@ ff_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
 }
 
-static size_t persist_smem_bytes(const TcGeom &G) {
-    const size_t a_res = G.a_resident ? (size_t)G.NKC * 16384 : 0, a_stage = G.a_resident ? 0 : 16384;
-    return 1024 + a_res + (size_t)G.nstages * ((size_t)G.NT * 128 + a_stage) + (size_t)TC_GROUPS * TC_CAP * 128 * 4 + sizeof(PsCtl) + 64;
+static size_t persist_smem_bytes(const TcGeom &G, int cap) {
+    const size_t a_res = G.a_resident ? (size_t)G.NKC * G.a_chunk_bytes : 0, a_stage = G.a_resident ? 0 : 16384;
+    return 1024 + a_res + (size_t)G.nstages * ((size_t)G.NT * 128 + a_stage) + (size_t)TC_GROUPS * cap * 128 * 4 + sizeof(PsCtl) + 64;
+}
+static int persist_fit_stages(TcGeom &G, int cap, int want) {
+    G.nstages = want;
+    while (persist_smem_bytes(G, cap) > 227 * 1024 && G.nstages > 2) G.nstages--;
+    return persist_smem_bytes(G, cap) <= 227 * 1024 ? G.nstages : 0;
 }
 
 // Persistent launch; TIMET_ERR_UNSUPPORTED if the shape does not qualify (caller falls back to the per-tile kernel)
@@ -466,30 +490,41 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
     // the epilogue keeps a lane's window as a 64-bit column mask and may read up to 3 TMEM columns past a key row whose
     // width is not a multiple of 4: wider grids / exactly filled buffers go to the per-item kernel
     if (G.W > 64 || ((G.W & 3) && G.NT + 3 > G.buf_cols)) return TIMET_ERR_UNSUPPORTED;
-    G.nstages = TC_MAX_STAGES;
     const EnvCfg &E = env_cfg();
     G.flags = E.tc_pflags;
-    if (E.tc_stages >= 2 && E.tc_stages <= TC_MAX_STAGES) G.nstages = E.tc_stages;
-    while (persist_smem_bytes(G) > 227 * 1024 && G.nstages > 2) G.nstages--;
-    if (persist_smem_bytes(G) > 227 * 1024) return TIMET_ERR_UNSUPPORTED;
-    const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
-    CUtensorMap map_a, map_b;
-    int rc;
     // column-blocked query tiles (see the kernel): grids 26..32 patches wide whose tiles are 4 grid rows, resident A.
     // TIMET_TC_PFLAGS & 256 keeps the raster tile.
     G.colblk = (G.a_resident && G.W >= 26 && G.W <= 32 && G.QR == 4 && !(G.flags & 256)) ? 1 : 0;
+    G.ncl = G.colblk ? G.W - 24 : 8;
+    // TIMET_TC_PFLAGS & 16384: padding rows kept inside every K chunk of A (16 KB apart) and 32-slot lists
+    const bool compact_a = G.colblk && !(G.flags & 16384);
+    G.a_chunk_bytes = compact_a ? (96 + 4 * G.ncl + 7) / 8 * 8 * 128 : 16384;
+    // Ring depth vs candidate-list capacity: the key ring is latency-bound (BASELINE configs[1]: two 28 KB stages beside
+    // A and 64 KB of lists), so 24-slot lists are used where the 16 KB they free buy a deeper ring (up to 4 stages).
+    const int want = (E.tc_stages >= 2 && E.tc_stages <= TC_MAX_STAGES) ? E.tc_stages : TC_MAX_STAGES;
+    const int st32 = persist_fit_stages(G, 32, want), st24 = persist_fit_stages(G, 24, want);
+    if (!st32 && !st24) return TIMET_ERR_UNSUPPORTED;
+    const int cap = (st24 > st32 && st32 < 4 && !(G.flags & 16384)) ? 24 : 32;
+    G.nstages = cap == 24 ? st24 : st32;
+    if (!G.nstages) return TIMET_ERR_UNSUPPORTED;
+    const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
+    CUtensorMap map_a, map_a3, map_b;
+    int rc;
     if (G.colblk) {
-        if ((rc = tc_make_map_colblk(&map_a, fn16, (int64_t)p.n_clips * p.n_frames * G.H, L.Dp, G.W)) != TIMET_OK) return rc;
+        if ((rc = tc_make_map_colblk(&map_a, fn16, (int64_t)p.n_clips * p.n_frames * G.H, L.Dp, G.W, 8)) != TIMET_OK) return rc;
+        if ((rc = tc_make_map_colblk(&map_a3, fn16, (int64_t)p.n_clips * p.n_frames * G.H, L.Dp, G.W, G.ncl)) != TIMET_OK) return rc;
     } else {
         if ((rc = tc_make_map(&map_a, fn16, L.rows + 256, L.Dp, 128)) != TIMET_OK) return rc;
+        map_a3 = map_a;
     }
     if ((rc = tc_make_map(&map_b, fn16, L.rows + 256, L.Dp, G.NT)) != TIMET_OK) return rc;
-    const size_t smem = persist_smem_bytes(G);
-    auto kern = E.tc_dyn ? ff_tc_persist_kernel<true> : ff_tc_persist_kernel<false>;
+    const size_t smem = persist_smem_bytes(G, cap);
+    auto kern = cap == 24 ? (E.tc_dyn ? ff_tc_persist_kernel<true, 24> : ff_tc_persist_kernel<false, 24>)
+                          : (E.tc_dyn ? ff_tc_persist_kernel<true, 32> : ff_tc_persist_kernel<false, 32>);
     TIMET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = G.total_tiles < num_sms() ? G.total_tiles : num_sms();
     unsigned int *next_item = reinterpret_cast<unsigned int *>(ws + L.off_redo + FF_HDR_NEXT_ITEM);   // zeroed with the redo header by timet_ff_select
-    kern<<<(unsigned)grid, TC_THREADS, smem, st>>>(map_a, map_b, G, reinterpret_cast<uint32_t *>(ws + L.off_cand),
+    kern<<<(unsigned)grid, TC_THREADS, smem, st>>>(map_a, map_a3, map_b, G, reinterpret_cast<uint32_t *>(ws + L.off_cand),
                                                                   reinterpret_cast<uint32_t *>(ws + L.off_cand_meta), next_item);
     TIMET_LAUNCHED();
     return TIMET_OK;

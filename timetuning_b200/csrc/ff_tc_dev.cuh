@@ -28,6 +28,8 @@ struct TcGeom {
     int clip_group;           // clips whose tiles are launched together (L2 locality); env TIMET_TC_CLIP_GROUP
     int flags;                // debug (env TIMET_TC_FLAGS): 1 = epilogue releases tiles unscanned, 2 = scan but never append
     int colblk;               // persistent kernel: query tile rows arranged as 4 column blocks of 4 x 8 queries (ff_tc3.cu)
+    int ncl;                  // ... valid columns of the last column block (W - 24): it is stored as 4 x ncl queries
+    int a_chunk_bytes;        // bytes between the 64-wide K chunks of the resident query tile (16384, or less: see ff_tc3.cu)
     int64_t total_tiles;
 };
 
@@ -178,6 +180,6 @@ __device__ __forceinline__ void tc_compact(uint32_t list, int &cnt, float &thr, 
 bool tc_geometry(const timet_ff_params &p, const FFLayout &L, TcGeom *G);
 size_t tc_smem_bytes(const TcGeom &G);
 int tc_make_map(CUtensorMap *m, const void *base, int64_t rows, int Dp, int box_rows);
-int tc_make_map_colblk(CUtensorMap *m, const void *base, int64_t grid_rows, int Dp, int grid_w);
+int tc_make_map_colblk(CUtensorMap *m, const void *base, int64_t grid_rows, int Dp, int grid_w, int box_cols);
 
 }  // namespace timet
