@@ -709,7 +709,7 @@ int ff_select_tc_launch(const timet_ff_params &p, const FFLayout &L, const float
         reinterpret_cast<unsigned long long *>(ws + L.off_stats), redo_list, redo_count, (uint32_t)L.queries);
     TIMET_LAUNCHED();
     // overflowed queries: exact scan (device-side count; a fixed small grid loops over the list)
-    if ((rc = ff_select_exact_run(p, L, feats, ws, redo_list, redo_count, (int64_t)num_sms() * 8 * 8, st)) != TIMET_OK) return rc;
+    if ((rc = ff_select_exact_run(p, L, feats, ws, redo_list, redo_count, (int64_t)num_sms() * 2 * 8, st)) != TIMET_OK) return rc;   // two CTAs per SM: the list is usually empty (grid-stride loop otherwise)
     return TIMET_OK;
 }
 
