@@ -27,7 +27,13 @@
 // 4 TMEM loads only, 8 oldest-first context order, 32 nanosleep back-off while polling tmem_full, 64 shared threshold read
 // once per tile instead of once per key row, 128 each TMEM buffer scanned by its own two groups only, 256 raster query tiles
 // (no column blocks), 512 epilogue waits for a key tile with a suspend-time hint, 1024 no final merge / publish, 2048 full lists are
-// emptied instead of compacted (1024 / 2048: timing attribution only, wrong results), 8192 no compaction while waiting for a key tile.
+// emptied instead of compacted (1024 / 2048: timing attribution only, wrong results), 8192 no compaction while waiting for a key tile,
+// 16384 padding rows inside every K chunk of A + 32-slot lists (two-stage key ring at 28 x 28 x 384), 32768 key rows always
+// top-down, bits 20+ entries appended before a waiting warp compacts (default 6).
+//
+// Shared-memory budget at BASELINE configs[1] (28 x 28, D = 384), 227 KB per CTA: query tile 84 KB (6 K chunks of 112 rows),
+// key ring 3 x 28 KB, candidate lists 4 groups x 24 slots x 128 queries x 4 B = 48 KB, control block 3.4 KB.  The ring is
+// latency-bound (bytes in flight per SM against ~1 us of TMA latency), so whatever fits goes to ring stages.
 #include <stdlib.h>
 
 #include "ff_tc_dev.cuh"
