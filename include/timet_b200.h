@@ -159,6 +159,12 @@ int timet_ff_tc_supported(const timet_ff_params *p);
  * 128-row MMA): the numerator of the tensor-pipe roofline in bench.py.  0 if the TC engine does not support the shape.
  * For comparison, the dense definition of SURVEY.md §8d is 2 * N^2 * dim * sum_t ctx(t) per clip. */
 double timet_ff_tc_executed_flops(const timet_ff_params *p);
+/* What timet_ff_select(TIMET_FF_TC / AUTO) will run for this problem (host-side query, no device work; honours the
+ * TIMET_TC_* experiment switches).  plan[8] = { kernel: 0 exact engine only, 1 per-item tcgen05 kernel, 2 persistent
+ * tcgen05 kernel; column-blocked query tiles (0/1); candidate-list slots per (query, group); key-ring stages; bytes of the
+ * resident query tile (0: streamed); key-tile columns; grid rows per query tile; dynamic shared memory in bytes }.
+ * The quantities behind the kernel's roofline in DESIGN.md §4.3; mask_propagation.py:418-436 is what they implement. */
+int timet_ff_tc_plan(const timet_ff_params *p, int32_t *plan);
 
 /* stage 1: one pass over the feature rows (F.normalize, :418-419): inverse norms + the fp16 tensor-core operand go to
  * the workspace.  No normalised fp32 copy is made: stage 2 reads `feats` IN PLACE for the exact fp32 similarity, so the

@@ -46,6 +46,56 @@ def test_workspace_queries_are_host_only():
     assert lib.timet_sinkhorn_workspace_bytes(25088, 200) > 200 * 4 * 300
 
 
+def _tc_plan(*args, **env):
+    """timet_ff_tc_plan for FFParams(*args) under the given TIMET_* switches (host-side query: no GPU needed)."""
+    import os
+    lib = _cabi.lib()
+    old = {k: os.environ.get(k) for k in env}
+    try:
+        for k, v in env.items():
+            os.environ[k] = v
+        lib.timet_debug_reload_env()
+        plan = (C.c_int32 * 8)()
+        assert lib.timet_ff_tc_plan(C.byref(_cabi.FFParams(*args)), plan) == 0
+        return dict(zip(("kernel", "colblk", "slots", "stages", "a_bytes", "key_cols", "tile_rows", "smem"), plan))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        lib.timet_debug_reload_env()
+
+
+def test_tc_plan_of_the_baseline_shapes():
+    """The persistent tcgen05 kernel's configuration is decided on the host: BASELINE configs[1] gets
+    column-blocked query tiles, an 84 KB query tile, 24-slot candidate lists and a three-stage key ring inside 227 KB."""
+    cfg2 = _tc_plan(32, 8, 28, 28, 384, 200, 7, 6, 5, 1, 0.1, 0)
+    assert cfg2 == dict(kernel=2, colblk=1, slots=24, stages=3, a_bytes=6 * 112 * 128, key_cols=224, tile_rows=4, smem=cfg2["smem"])
+    assert cfg2["smem"] <= 227 * 1024
+    # the switch that keeps the padding rows inside every K chunk: 96 KB query tile, 32-slot lists, two stages
+    old = _tc_plan(32, 8, 28, 28, 384, 200, 7, 6, 5, 1, 0.1, 0, TIMET_TC_PFLAGS="16384")
+    assert (old["colblk"], old["slots"], old["stages"], old["a_bytes"]) == (1, 32, 2, 6 * 16384)
+    raster = _tc_plan(32, 8, 28, 28, 384, 200, 7, 6, 5, 1, 0.1, 0, TIMET_TC_PFLAGS="256")
+    assert (raster["colblk"], raster["slots"], raster["stages"], raster["a_bytes"]) == (0, 32, 2, 6 * 16384)
+    # configs[0] (14 x 14), configs[3] (60 x 60, radius 12, k 7), configs[4] (56 x 56, D = 768: streamed query tile)
+    cfg1 = _tc_plan(2, 4, 14, 14, 384, 200, 7, 6, 5, 1, 0.1, 0)
+    assert (cfg1["kernel"], cfg1["colblk"], cfg1["tile_rows"]) == (2, 0, 9)
+    cfg4 = _tc_plan(1, 80, 60, 60, 384, 11, 7, 12, 7, 1, 0.1, 0)
+    assert (cfg4["kernel"], cfg4["colblk"], cfg4["key_cols"], cfg4["tile_rows"]) == (2, 0, 240, 2)
+    cfg5 = _tc_plan(8, 16, 56, 56, 768, 300, 7, 6, 5, 1, 0.1, 0)
+    assert (cfg5["kernel"], cfg5["colblk"], cfg5["a_bytes"], cfg5["key_cols"]) == (2, 0, 0, 224)
+    for c in (cfg1, cfg4, cfg5):
+        assert c["smem"] <= 227 * 1024 and c["stages"] >= 2
+    # other column-blocked widths: the last column block holds W - 24 columns
+    for W, rows in ((26, 104), (30, 120), (32, 128)):
+        pl = _tc_plan(2, 4, 12, W, 128, 8, 7, 3, 5, 1, 0.1, 0)
+        assert (pl["colblk"], pl["a_bytes"]) == (1, 2 * rows * 128), (W, pl)
+    # per-item kernel / exact engine
+    assert _tc_plan(32, 8, 28, 28, 384, 200, 7, 6, 5, 1, 0.1, 0, TIMET_TC_PERSIST="0")["kernel"] == 1
+    assert _tc_plan(2, 4, 28, 28, 384, 200, 7, 6, 12, 1, 0.1, 0)["kernel"] == 0          # top-k 12: exact engine
+
+
 @pytest.mark.parametrize("field,value", [("n_clips", 0), ("n_frames", 1), ("topk", 0), ("topk", 17), ("n_last_frames", 0),
                                          ("t_begin", 0), ("t_begin", 8), ("radius", -1), ("temperature", 0.0), ("dim", 0)])
 def test_ff_validation(field, value):

@@ -45,6 +45,7 @@ _PROTOS = {
     "timet_ff_workspace_bytes": (C.c_size_t, [C.POINTER(FFParams)]),
     "timet_ff_tc_supported": (C.c_int, [C.POINTER(FFParams)]),
     "timet_ff_tc_executed_flops": (C.c_double, [C.POINTER(FFParams)]),
+    "timet_ff_tc_plan": (C.c_int, [C.POINTER(FFParams), _P]),
     "timet_ff_prepare": (C.c_int, [C.POINTER(FFParams), _P, _P, C.c_size_t, _P]),
     "timet_ff_select": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, _P, C.c_size_t, _P]),
     "timet_ff_select_timed": (C.c_int, [C.POINTER(FFParams), C.c_int, _P, _P, C.c_size_t, _P, _P, _P]),

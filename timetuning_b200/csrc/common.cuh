@@ -154,6 +154,7 @@ int ff_gather_launch(const timet_ff_params &p, const FFLayout &L, float *labels,
                      cudaStream_t st);
 bool ff_tc_supported(const timet_ff_params &p);
 double ff_tc_executed_flops(const timet_ff_params &p);
+int ff_tc_plan(const timet_ff_params &p, int32_t *out);
 int ff_tc_debug_trace(const timet_ff_params &p, const FFLayout &L, const char *ws, unsigned long long *out, int n_ctas, cudaStream_t st);
 int ff_tc_debug_tile(const timet_ff_params &p, const FFLayout &L, char *ws, int64_t tile_id, float *dump, cudaStream_t st);
 

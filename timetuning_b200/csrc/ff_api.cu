@@ -54,6 +54,12 @@ double timet_ff_tc_executed_flops(const timet_ff_params *p) {
     return ff_tc_executed_flops(*p);
 }
 
+int timet_ff_tc_plan(const timet_ff_params *p, int32_t *plan) {
+    if (ff_validate(p) != TIMET_OK) return TIMET_ERR_INVALID;
+    TIMET_CHECK_ARG(plan != nullptr, "ff_tc_plan: plan is NULL");
+    return ff_tc_plan(*p, plan);
+}
+
 int timet_ff_prepare(const timet_ff_params *p, const float *feats, void *workspace, size_t workspace_bytes,
                      timet_stream_t stream) {
     FFLayout L;

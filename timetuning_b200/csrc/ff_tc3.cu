@@ -489,9 +489,9 @@ static int persist_fit_stages(TcGeom &G, int cap, int want) {
     return persist_smem_bytes(G, cap) <= 227 * 1024 ? G.nstages : 0;
 }
 
-// Persistent launch; TIMET_ERR_UNSUPPORTED if the shape does not qualify (caller falls back to the per-tile kernel)
-int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
-    TcGeom G;
+// Configuration of the persistent kernel for a problem (host only, no CUDA call): query-tile layout, candidate-list
+// capacity, key-ring depth.  TIMET_ERR_UNSUPPORTED if the shape does not qualify (the per-item kernel takes it).
+static int persist_configure(const timet_ff_params &p, const FFLayout &L, TcGeom &G, int *cap_out) {
     if (!tc_geometry(p, L, &G)) return TIMET_ERR_UNSUPPORTED;
     // the epilogue keeps a lane's window as a 64-bit column mask and may read up to 3 TMEM columns past a key row whose
     // width is not a multiple of 4: wider grids / exactly filled buffers go to the per-item kernel
@@ -513,6 +513,39 @@ int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, cha
     const int cap = (st24 > st32 && st32 < 4 && !(G.flags & 16384)) ? 24 : 32;
     G.nstages = cap == 24 ? st24 : st32;
     if (!G.nstages) return TIMET_ERR_UNSUPPORTED;
+    *cap_out = cap;
+    return TIMET_OK;
+}
+
+// timet_ff_tc_plan: what ff_select will run for this problem
+int ff_tc_plan(const timet_ff_params &p, int32_t *out) {
+    const FFLayout L = ff_layout(p);
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    TcGeom G;
+    if (!tc_geometry(p, L, &G)) return TIMET_OK;               // exact engine
+    const EnvCfg &E = env_cfg();
+    int cap = 32;
+    const bool debug = E.tc_trace || E.tc_flags != 0;
+    if (E.tc_persist && !debug && persist_configure(p, L, G, &cap) == TIMET_OK) {
+        out[0] = 2; out[1] = G.colblk; out[2] = cap; out[3] = G.nstages; out[4] = G.a_resident ? G.NKC * G.a_chunk_bytes : 0;
+        out[5] = G.NT; out[6] = G.QR; out[7] = (int32_t)persist_smem_bytes(G, cap);
+        return TIMET_OK;
+    }
+    if (!tc_geometry(p, L, &G)) return TIMET_OK;
+    out[0] = 1; out[2] = TC_CAP; out[3] = G.nstages; out[4] = G.a_resident ? G.NKC * 16384 : 0; out[5] = G.NT; out[6] = G.QR;
+    out[7] = (int32_t)tc_smem_bytes(G);
+    return TIMET_OK;
+}
+
+// Persistent launch; TIMET_ERR_UNSUPPORTED if the shape does not qualify (caller falls back to the per-tile kernel)
+int ff_select_tc_persist_launch(const timet_ff_params &p, const FFLayout &L, char *ws, cudaStream_t st) {
+    TcGeom G;
+    int cap = 32;
+    {
+        const int rc0 = persist_configure(p, L, G, &cap);
+        if (rc0 != TIMET_OK) return rc0;
+    }
+    const EnvCfg &E = env_cfg();
     const __half *fn16 = reinterpret_cast<const __half *>(ws + L.off_fn16);
     CUtensorMap map_a, map_a3, map_b;
     int rc;
